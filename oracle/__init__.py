@@ -1,0 +1,46 @@
+"""CPU oracle for the pointwise-downscaling hot path — TEST INFRASTRUCTURE ONLY.
+
+This package is a plain-numpy restatement of the algorithms that
+pangeo-data/scikit-downscale runs per grid cell (reference files cited per
+function as ``skdownscale/pointwise_models/<file>:<lines>``).  It exists so the
+CUDA path can be checked on machines where ``/root/reference`` is absent (the
+GPU box).  It is NOT part of the product:
+
+* only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+  ``cpu_baseline`` / ``--impl reference`` legs may import it;
+* the product (``scikit-downscale_b200``) never imports it and has no CPU
+  fallback — it fails loudly when the CUDA library is missing.
+
+Parity pin: the oracle is asserted against the LIVE reference estimators
+(imported from ``/root/reference`` in the build container) through the golden
+vectors committed under ``tests/golden/`` (generator:
+``tests/golden/make_golden.py``) and against the reference's own known-answer
+tests (``skdownscale/test/test_pointwise_models.py:81-90`` quantile mapper,
+``:302-312`` padded DOY grouper) — see ``tests/test_oracle_golden.py``.
+"""
+
+from .groupers import (  # noqa: F401
+    day_keys,
+    groups_from_keys,
+    month_keys,
+    padded_doy_groups,
+)
+from .quantile import (  # noqa: F401
+    cunnane_inverse,
+    plotting_positions,
+    quantile_mapper_fit,
+    quantile_mapper_transform,
+    rank_max_ties,
+)
+from .bcsd import (  # noqa: F401
+    bcsd_precipitation_fit,
+    bcsd_precipitation_predict,
+    bcsd_temperature_fit,
+    bcsd_temperature_predict,
+)
+from .gard import (  # noqa: F401
+    analog_regression_predict,
+    knn_bruteforce,
+    pure_analog_predict,
+)
+from .wrapper import pointwise_fit_predict  # noqa: F401

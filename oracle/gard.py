@@ -1,0 +1,124 @@
+"""Oracle: GARD analog models for ONE cell (TEST INFRASTRUCTURE — see oracle/__init__.py).
+
+Follows skdownscale/pointwise_models/gard.py:58-87 (AnalogBase.fit),
+:273-364 (PureAnalog.predict) and :152-224 (AnalogRegression.predict /
+_predict_one_step, thresh=None).  The neighbour search of
+sklearn.neighbors.KDTree (scikit-learn, pinned 1.7.2 in the reference's
+uv.lock:3033-3034; not vendored) is restated as an exact float64 brute force:
+squared Euclidean distance accumulated feature by feature, neighbours in
+ascending distance, lowest train index first on exact ties (KDTree's own tie
+order is implementation-defined, so parity inputs are tie-free).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def knn_bruteforce(X_train: np.ndarray, X_query: np.ndarray, k: int):
+    """``KDTree(X_train).query(X_query, k)`` (gard.py:82,194,299).
+
+    Returns (dist float64 [Tq,k], inds int64 [Tq,k]).  Distances are
+    ``sqrt(sum_j (q_j - a_j)**2)`` with the sum taken j = 0..p-1 in order, in
+    float64 (KDTree copies its data to float64)."""
+    A = np.asarray(X_train, dtype=np.float64)
+    Q = np.asarray(X_query, dtype=np.float64)
+    if A.ndim == 1:
+        A = A[:, None]
+    if Q.ndim == 1:
+        Q = Q[:, None]
+    Tq = Q.shape[0]
+    dist = np.empty((Tq, k), dtype=np.float64)
+    inds = np.empty((Tq, k), dtype=np.int64)
+    for i in range(Tq):
+        d2 = np.zeros(A.shape[0], dtype=np.float64)
+        for j in range(A.shape[1]):
+            diff = Q[i, j] - A[:, j]
+            d2 = d2 + diff * diff
+        order = np.argsort(d2, kind='stable')[:k]
+        inds[i] = order
+        dist[i] = np.sqrt(d2[order])
+    return dist, inds
+
+
+def pure_analog_predict(X_train, y_train, X_query, n_analogs: int = 200, kind: str = 'best_analog',
+                        thresh=None, rand_inds=None, return_inds: bool = False):
+    """PureAnalog.fit + predict (gard.py:58-87, 273-364).
+
+    Returns float64 [Tq, 3] in ``output_names`` order (pred, exceedance_prob,
+    prediction_error); the individual columns are first computed in the dtypes
+    the reference produces (pred/err in y's dtype for best/mean, float64 for
+    weight) and then widened exactly.  ``rand_inds`` replaces the global-RNG draw
+    ``np.random.randint(0, k, size=Tq)`` of gard.py:315 for 'sample_analogs'.
+    """
+    y_ = np.asarray(y_train).reshape(-1)
+    Tq = len(np.asarray(X_query))
+    k_ = min(n_analogs, len(y_))                                    # gard.py:75-79
+    if kind == 'best_analog' or n_analogs == 1:                     # gard.py:290-296
+        k, kind = 1, 'best_analog'
+    else:
+        k = k_
+    dist, inds = knn_bruteforce(X_train, X_query, k)                # gard.py:299
+    analogs = np.take(y_, inds, axis=0)                             # gard.py:301
+    if thresh is not None:                                          # gard.py:303-308
+        analog_mask = analogs > thresh
+        masked = np.where(analog_mask, analogs, np.nan)
+    if kind == 'best_analog':
+        predicted = analogs[:, 0]
+    elif kind == 'sample_analogs':
+        if rand_inds is None:
+            raise ValueError('sample_analogs needs the host-drawn rand_inds')
+        predicted = analogs[np.arange(Tq), np.asarray(rand_inds)].astype(np.float64)   # gard.py:19-24
+    elif kind == 'weight_analogs':
+        weights = 1.0 / np.where(dist == 0, 1e-20, dist)            # gard.py:322-323
+        src = masked if thresh is not None else analogs
+        predicted = np.average(src, weights=weights, axis=1)        # gard.py:324-327
+    elif kind == 'mean_analogs':
+        predicted = (masked if thresh is not None else analogs).mean(axis=1)   # gard.py:329-333
+    else:
+        raise ValueError(f'got unexpected kind {kind}')
+    if thresh is not None:                                          # gard.py:338-343
+        predicted = np.nan_to_num(predicted, nan=0.0)
+        prediction_error = masked.std(axis=1)
+        exceedance_prob = np.where(analog_mask, 1, 0).mean(axis=1)
+    else:                                                           # gard.py:344-346
+        prediction_error = analogs.std(axis=1)
+        exceedance_prob = np.ones(Tq, dtype=np.float64)
+    out = np.stack([np.asarray(predicted, dtype=np.float64),
+                    np.asarray(exceedance_prob, dtype=np.float64),
+                    np.asarray(prediction_error, dtype=np.float64)], axis=1)
+    return (out, inds, dist) if return_inds else out
+
+
+def analog_regression_predict(X_train, y_train, X_query, n_analogs: int = 200, thresh=None,
+                              return_inds: bool = False):
+    """AnalogRegression.fit + predict with thresh=None (gard.py:152-224).
+
+    Per timestep: k nearest analogs → ordinary least squares with intercept on
+    the float64 analog predictors (sklearn LinearRegression = centred
+    ``lstsq``, minimum-norm when rank deficient) → prediction at the query
+    point, exceedance_prob = 1.0, prediction_error = in-sample RMSE."""
+    if thresh is not None:
+        raise NotImplementedError('AnalogRegression(thresh=...) needs the logistic step (SURVEY §8f row 4)')
+    A = np.asarray(X_train, dtype=np.float64)
+    if A.ndim == 1:
+        A = A[:, None]
+    Q = np.asarray(X_query)
+    if Q.ndim == 1:
+        Q = Q[:, None]
+    y_ = np.asarray(y_train).reshape(-1)
+    k_ = min(n_analogs, len(y_))
+    _, inds = knn_bruteforce(A, Q, k_)                              # gard.py:194
+    out = np.empty((Q.shape[0], 3), dtype=np.float64)
+    for i in range(Q.shape[0]):
+        x = A[inds[i]]                                              # gard.py:197
+        y = y_[inds[i]].astype(np.float64)                          # gard.py:198 (+ sklearn cast)
+        xo = x.mean(axis=0)
+        yo = y.mean()
+        coef, *_ = np.linalg.lstsq(x - xo, y - yo, rcond=None)      # gard.py:215
+        intercept = yo - xo @ coef
+        y_hat = x @ coef + intercept                                # gard.py:218
+        err = np.sqrt(np.mean((y - y_hat) ** 2))                    # gard.py:219
+        pred = Q[i].astype(np.float64) @ coef + intercept           # gard.py:221
+        out[i] = (pred, 1.0, err)                                   # gard.py:224
+    return (out, inds) if return_inds else out

@@ -1,0 +1,214 @@
+"""Generate the golden vectors under tests/golden/ by running the LIVE reference.
+
+Run in the build container only (``/root/reference`` is not on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference package ``__init__`` imports xarray (absent here), so the
+per-cell estimator modules are imported with stub parent packages (SURVEY.md
+Appendix C); the ``PointWiseDownscaler`` cell loop (core.py:69-143) is restated
+in ``_cell_loop`` below (deepcopy → fit → predict → squeeze → cast to X.dtype).
+Versions used are recorded in tests/golden/VERSIONS.json.
+"""
+
+from __future__ import annotations
+
+import copy
+import importlib
+import json
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import pandas as pd
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import synth  # noqa: E402
+
+REF = '/root/reference/skdownscale'
+
+
+def load_reference():
+    for name, path in [('skdownscale', REF), ('skdownscale.pointwise_models', REF + '/pointwise_models')]:
+        m = types.ModuleType(name)
+        m.__path__ = [path]
+        sys.modules[name] = m
+    mods = {}
+    for sub in ('bcsd', 'quantile', 'gard', 'groupers'):
+        mods[sub] = importlib.import_module(f'skdownscale.pointwise_models.{sub}')
+    return mods
+
+
+def _df(a, index=None):
+    a = np.asarray(a)
+    if a.ndim == 1:
+        a = a[:, None]
+    cols = [f'f{i}' for i in range(a.shape[1])]
+    return pd.DataFrame(a, columns=cols, index=index)
+
+
+def _cell_loop(model, Xtr, ytr, Xp, index_fit=None, index_pred=None, n_outputs=1):
+    """core.py:69-143 for arrays [T, C] or [T, p, C]."""
+    C = Xp.shape[-1]
+    Tp = Xp.shape[0]
+    out = np.full((Tp, n_outputs, C) if n_outputs > 1 else (Tp, C), np.nan, dtype=Xp.dtype)
+    for c in range(C):
+        first = Xtr[0, 0, c] if Xtr.ndim == 3 else Xtr[0, c]
+        if np.isnan(first):
+            continue
+        mod = copy.deepcopy(model)
+        xdf = _df(Xtr[..., c], index_fit)
+        ydf = _df(ytr[:, c], index_fit)
+        mod.fit(xdf, ydf)
+        res = mod.predict(_df(Xp[..., c], index_pred))
+        res = np.asarray(res).squeeze()
+        if n_outputs > 1:
+            out[:, :, c] = res
+        else:
+            out[:, c] = res
+    return out
+
+
+def save(name, **arrays):
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
+    print('wrote', name, {k: getattr(v, 'shape', None) for k, v in arrays.items()})
+
+
+def main():
+    warnings.simplefilter('ignore')
+    ref = load_reference()
+    QuantileMapper = ref['quantile'].QuantileMapper
+    BcsdTemperature = ref['bcsd'].BcsdTemperature
+    BcsdPrecipitation = ref['bcsd'].BcsdPrecipitation
+    PureAnalog = ref['gard'].PureAnalog
+    AnalogRegression = ref['gard'].AnalogRegression
+    PaddedDOYGrouper = ref['groupers'].PaddedDOYGrouper
+
+    # --- 1. the reference's own known-answer test (test_pointwise_models.py:81-90)
+    n = 100
+    expected = (np.sin(np.linspace(-10 * np.pi, 10 * np.pi, n)) * 10).reshape(-1, 1)
+    with_bias = expected + 2
+    actual = QuantileMapper().fit(expected).transform(with_bias)
+    np.testing.assert_almost_equal(actual, expected)
+    save('qm_known_answer', fit=expected, x=with_bias, out=actual)
+
+    # --- 2. QuantileMapper on whole series, several length relations, ties, dtypes
+    def qm_case(name, Tf, Tp, C, seed, dtype=np.float32, quant=None):
+        _, ytr, _ = synth.temperature(Tf, C, seed, dtype)
+        _, _, Xp = synth.temperature(Tp, C, seed + 100, dtype)
+        if quant:
+            ytr = (np.round(ytr / quant) * quant).astype(dtype)
+            Xp = (np.round(Xp / quant) * quant).astype(dtype)
+        out = np.empty((Tp, C), dtype=np.float64)
+        for c in range(C):
+            out[:, c] = QuantileMapper().fit(ytr[:, c:c + 1]).transform(Xp[:, c:c + 1])[:, 0]
+        save(name, ytr=ytr, Xp=Xp, out=out)
+
+    qm_case('qm_equal_len', 730, 730, 3, 10)
+    qm_case('qm_pred_longer', 365, 1000, 3, 11)      # exercises both OLS tails
+    qm_case('qm_pred_shorter', 1000, 300, 3, 12)
+    qm_case('qm_ties', 500, 700, 3, 13, quant=0.5)   # heavy ties, max-rank rule
+    qm_case('qm_f64', 400, 450, 2, 14, dtype=np.float64)
+    qm_case('qm_tiny', 7, 25, 2, 15)                 # fewer fit points than n_endpoints
+
+    # --- 3. BcsdTemperature, monthly groups
+    def bcsd_t_case(name, Tf, Tp, C, seed, start_fit='1981-01-01', start_pred=None, dtype=np.float32,
+                    nan_cells=(), **kw):
+        idx_f = synth.daily_index(Tf, start_fit)
+        idx_p = synth.daily_index(Tp, start_pred or start_fit)
+        Xtr, ytr, _ = synth.temperature(Tf, C, seed, dtype)
+        _, _, Xp = synth.temperature(Tp, C, seed + 100, dtype)
+        for c in nan_cells:
+            Xtr[:, c] = np.nan
+            ytr[:, c] = np.nan
+            Xp[:, c] = np.nan
+        out = _cell_loop(BcsdTemperature(**kw), Xtr, ytr, Xp, idx_f, idx_p)
+        out64 = np.full((Tp, C), np.nan)
+        for c in range(C):
+            if np.isnan(Xtr[0, c]):
+                continue
+            m = BcsdTemperature(**kw).fit(_df(Xtr[:, c], idx_f), _df(ytr[:, c], idx_f))
+            out64[:, c] = m.predict(_df(Xp[:, c], idx_p)).values[:, 0]
+        save(name, Xtr=Xtr, ytr=ytr, Xp=Xp, out=out, out64=out64,
+             start_fit=np.array(start_fit), start_pred=np.array(start_pred or start_fit))
+
+    bcsd_t_case('bcsd_t_month_anoms', 1461, 1461, 4, 20, nan_cells=(2,))
+    bcsd_t_case('bcsd_t_month_abs', 1461, 1461, 3, 21, return_anoms=False)
+    bcsd_t_case('bcsd_t_month_future', 1461, 2192, 3, 22, start_pred='1985-01-01')   # T_pred > T_fit → tails
+    bcsd_t_case('bcsd_t_month_f64', 1096, 1096, 2, 23, dtype=np.float64)
+    bcsd_t_case('bcsd_t_month_30yr', 10950, 10950, 1, 0)                              # BASELINE config[0]
+    bcsd_t_case('bcsd_t_nasanex', 1096, 1096, 2, 24, start_fit='1980-01-01',
+                time_grouper='daily_nasa-nex', return_anoms=False)
+
+    # --- 4. BcsdPrecipitation
+    def bcsd_p_case(name, Tf, Tp, C, seed, start_fit='1981-01-01', start_pred=None, **kw):
+        idx_f = synth.daily_index(Tf, start_fit)
+        idx_p = synth.daily_index(Tp, start_pred or start_fit)
+        Xtr, ytr, _ = synth.precipitation(Tf, C, seed)
+        _, _, Xp = synth.precipitation(Tp, C, seed + 100)
+        out = _cell_loop(BcsdPrecipitation(**kw), Xtr, ytr, Xp, idx_f, idx_p)
+        out64 = np.empty((Tp, C))
+        for c in range(C):
+            m = BcsdPrecipitation(**kw).fit(_df(Xtr[:, c], idx_f), _df(ytr[:, c], idx_f))
+            out64[:, c] = m.predict(_df(Xp[:, c], idx_p)).values[:, 0]
+        save(name, Xtr=Xtr, ytr=ytr, Xp=Xp, out=out, out64=out64,
+             start_fit=np.array(start_fit), start_pred=np.array(start_pred or start_fit))
+
+    bcsd_p_case('bcsd_p_month_anoms', 1461, 1461, 3, 30)
+    bcsd_p_case('bcsd_p_month_abs_future', 1096, 1461, 3, 31, start_pred='1984-01-01', return_anoms=False)
+    bcsd_p_case('bcsd_p_nasanex', 1096, 1096, 2, 32, start_fit='1980-01-01',
+                time_grouper='daily_nasa-nex', return_anoms=False)
+
+    # --- 5. PaddedDOYGrouper membership (test_pointwise_models.py:302-312) + full table
+    index = pd.date_range(start='1980-01-01', end='1982-12-31')
+    Xg = pd.DataFrame({'foo': np.arange(len(index), dtype=np.float64)}, index=index)
+    groups = dict(list(PaddedDOYGrouper(Xg)))
+    np.testing.assert_array_equal(np.unique(groups[123].index.dayofyear), np.arange(108, 139))
+    lens = np.array([len(groups[d]) for d in range(1, 367)])
+    rows = np.full((366, lens.max()), -1, dtype=np.int64)
+    for d in range(1, 367):
+        rows[d - 1, :lens[d - 1]] = groups[d]['foo'].values.astype(np.int64)
+    save('padded_doy_1980_1982', rows=rows, lens=lens)
+
+    # --- 6. GARD
+    def pure_case(name, T, Tq, C, seed, n_analogs, kind, thresh=None):
+        Xtr, ytr, Xq = synth.analog(T, Tq, C, 3, seed)
+        rand = None
+        if kind == 'sample_analogs':
+            np.random.seed(1234)          # the reference draws from the GLOBAL numpy RNG (gard.py:315)
+            rand = np.stack([np.random.randint(0, n_analogs, size=Tq) for _ in range(C)], axis=1)
+            np.random.seed(1234)
+        out = _cell_loop(PureAnalog(n_analogs=n_analogs, kind=kind, thresh=thresh), Xtr, ytr, Xq, n_outputs=3)
+        kw = dict(Xtr=Xtr, ytr=ytr, Xq=Xq, out=out)
+        if rand is not None:
+            kw['rand'] = rand
+        save(name, **kw)
+
+    for kind in ('best_analog', 'mean_analogs', 'weight_analogs', 'sample_analogs'):
+        pure_case(f'pure_{kind}', 400, 150, 2, 40, 10, kind)
+        pure_case(f'pure_{kind}_thresh', 400, 150, 2, 41, 10, kind, thresh=0.0)
+    pure_case('pure_mean_analogs_k200', 500, 60, 1, 42, 200, 'mean_analogs')
+
+    def ar_case(name, T, Tq, C, seed, n_analogs):
+        Xtr, ytr, Xq = synth.analog(T, Tq, C, 3, seed)
+        out = _cell_loop(AnalogRegression(n_analogs=n_analogs), Xtr, ytr, Xq, n_outputs=3)
+        out64 = np.empty((Tq, 3, C))
+        for c in range(C):
+            m = AnalogRegression(n_analogs=n_analogs).fit(_df(Xtr[..., c]), _df(ytr[:, c]))
+            out64[:, :, c] = np.asarray(m.predict(_df(Xq[..., c])))
+        save(name, Xtr=Xtr, ytr=ytr, Xq=Xq, out=out, out64=out64)
+
+    ar_case('analogreg_k10', 300, 120, 2, 50, 10)
+    ar_case('analogreg_k200', 400, 40, 1, 51, 200)
+
+    import sklearn
+    with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
+        json.dump({'numpy': np.__version__, 'pandas': pd.__version__, 'sklearn': sklearn.__version__,
+                   'reference': 'pangeo-data/scikit-downscale @ 44d0425 (/root/reference)'}, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()

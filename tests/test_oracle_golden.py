@@ -1,0 +1,146 @@
+"""The numpy oracle (oracle/) against the golden vectors produced by the LIVE reference
+(tests/golden/make_golden.py).  CPU only.  Tolerances: the oracle restates float64
+arithmetic, so it must agree with the reference far tighter than the 1e-5 product bar."""
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import oracle
+import synth
+
+
+def _close(a, b, rtol=1e-12, atol=1e-12):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, equal_nan=True)
+
+
+def test_qm_known_answer(golden):
+    g = golden('qm_known_answer')            # skdownscale/test/test_pointwise_models.py:81-90
+    st = oracle.quantile_mapper_fit(g['fit'][:, 0])
+    out = oracle.quantile_mapper_transform(g['x'][:, 0], st)
+    np.testing.assert_almost_equal(out, g['fit'][:, 0])
+    _close(out, g['out'][:, 0])
+
+
+@pytest.mark.parametrize('name', ['qm_equal_len', 'qm_pred_longer', 'qm_pred_shorter', 'qm_ties',
+                                  'qm_f64', 'qm_tiny'])
+def test_qm_cases(golden, name):
+    g = golden(name)
+    out = oracle.pointwise_fit_predict({'name': 'QuantileMapper'}, None, g['ytr'], g['Xp'])
+    _close(out, g['out'].astype(g['Xp'].dtype))
+    for c in range(g['Xp'].shape[1]):
+        st = oracle.quantile_mapper_fit(g['ytr'][:, c])
+        _close(oracle.quantile_mapper_transform(g['Xp'][:, c], st), g['out'][:, c], rtol=1e-13, atol=1e-13)
+
+
+def test_plotting_positions_and_rank():
+    pp = oracle.plotting_positions(5)
+    _close(pp, (np.arange(1, 6) - 0.4) / (((5 + 1.0) - 0.4) - 0.4), rtol=0, atol=0)   # NOT 5.2: evaluation order matters
+    r = oracle.rank_max_ties(np.array([3.0, 1.0, 3.0, 2.0, 1.0]))
+    assert r.tolist() == [5, 2, 5, 3, 2]
+
+
+def test_padded_doy_grouper(golden):
+    g = golden('padded_doy_1980_1982')       # test_pointwise_models.py:302-312 + full table
+    index = pd.date_range(start='1980-01-01', end='1982-12-31')
+    groups = oracle.padded_doy_groups(index)
+    assert len(groups) == 366
+    for (key, rows), ref_rows, n in zip(groups, g['rows'], g['lens']):
+        assert len(rows) == n
+        np.testing.assert_array_equal(rows, ref_rows[:n])
+    doy = np.asarray(index.dayofyear)
+    np.testing.assert_array_equal(np.unique(doy[groups[122][1]]), np.arange(108, 139))
+    # the irregular DOY-366 group: non-leap rows are DOYs 351..365 and 2..15
+    rows366 = groups[365][1]
+    nl = rows366[~np.asarray(index.is_leap_year)[rows366]]
+    assert sorted(set(doy[nl].tolist())) == list(range(2, 16)) + list(range(351, 366))
+
+
+@pytest.mark.parametrize('name,kw', [
+    ('bcsd_t_month_anoms', {}),
+    ('bcsd_t_month_abs', {'return_anoms': False}),
+    ('bcsd_t_month_future', {}),
+    ('bcsd_t_month_f64', {}),
+    ('bcsd_t_month_30yr', {}),
+    ('bcsd_t_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
+])
+def test_bcsd_temperature(golden, name, kw):
+    g = golden(name)
+    idx_f = synth.daily_index(len(g['Xtr']), str(g['start_fit']))
+    idx_p = synth.daily_index(len(g['Xp']), str(g['start_pred']))
+    spec = {'name': 'BcsdTemperature', 'time_grouper': 'month', **kw}
+    out = oracle.pointwise_fit_predict(spec, g['Xtr'], g['ytr'], g['Xp'], idx_f, idx_p)
+    assert out.dtype == g['Xp'].dtype
+    ref = g['out64']
+    scale = np.nanstd(g['ytr'])
+    assert np.nanmax(np.abs(out.astype(np.float64) - ref.astype(g['Xp'].dtype))) <= 1e-6 * scale
+    # float64 agreement of the unrounded result, cell by cell
+    fit_groups, roll_groups, qm_groups = oracle.wrapper._bcsd_groups(spec['time_grouper'], idx_f, idx_p)
+    for c in range(g['Xp'].shape[1]):
+        if np.isnan(g['Xtr'][0, c]):
+            assert np.isnan(out[:, c]).all() and np.isnan(g['out'][:, c]).all()
+            continue
+        how = 'frame' if spec['time_grouper'] == 'daily_nasa-nex' else 'groupby'
+        st = oracle.bcsd_temperature_fit(g['Xtr'][:, c], g['ytr'][:, c], fit_groups, how)
+        o = oracle.bcsd_temperature_predict(st, g['Xp'][:, c], roll_groups, qm_groups,
+                                            kw.get('return_anoms', True))
+        _close(o, ref[:, c], rtol=0, atol=2e-12 * max(1.0, scale))
+
+
+@pytest.mark.parametrize('name,kw', [
+    ('bcsd_p_month_anoms', {}),
+    ('bcsd_p_month_abs_future', {'return_anoms': False}),
+    ('bcsd_p_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
+])
+def test_bcsd_precipitation(golden, name, kw):
+    g = golden(name)
+    idx_f = synth.daily_index(len(g['Xtr']), str(g['start_fit']))
+    idx_p = synth.daily_index(len(g['Xp']), str(g['start_pred']))
+    spec = {'name': 'BcsdPrecipitation', 'time_grouper': 'month', **kw}
+    out = oracle.pointwise_fit_predict(spec, g['Xtr'], g['ytr'], g['Xp'], idx_f, idx_p)
+    _close(out, g['out'], rtol=1e-6, atol=0)
+    fit_groups, _, qm_groups = oracle.wrapper._bcsd_groups(spec['time_grouper'], idx_f, idx_p)
+    for c in range(g['Xp'].shape[1]):
+        how = 'frame' if spec['time_grouper'] == 'daily_nasa-nex' else 'groupby'
+        st = oracle.bcsd_precipitation_fit(g['ytr'][:, c], fit_groups, kw.get('return_anoms', True), how)
+        o = oracle.bcsd_precipitation_predict(st, g['Xp'][:, c], qm_groups, kw.get('return_anoms', True))
+        _close(o, g['out64'][:, c], rtol=1e-13, atol=1e-13)
+
+
+def test_bcsd_precipitation_bad_climatology():
+    idx = synth.daily_index(400)
+    y = np.zeros(400, dtype=np.float32)
+    groups = oracle.groups_from_keys(oracle.month_keys(idx))
+    with pytest.raises(ValueError, match='Invalid value in target climatology'):
+        oracle.bcsd_precipitation_fit(y, groups, True)
+
+
+@pytest.mark.parametrize('kind', ['best_analog', 'mean_analogs', 'weight_analogs', 'sample_analogs'])
+@pytest.mark.parametrize('suffix,thresh', [('', None), ('_thresh', 0.0)])
+def test_pure_analog(golden, kind, suffix, thresh):
+    g = golden(f'pure_{kind}{suffix}')
+    spec = {'name': 'PureAnalog', 'n_analogs': 10, 'kind': kind, 'thresh': thresh}
+    C = g['Xq'].shape[-1]
+    for c in range(C):
+        rand = g['rand'][:, c] if 'rand' in g else None
+        o = oracle.pure_analog_predict(g['Xtr'][..., c], g['ytr'][:, c], g['Xq'][..., c], 10, kind, thresh, rand)
+        _close(o.astype(np.float32), g['out'][:, :, c], rtol=2e-6, atol=1e-7)
+    if 'rand' not in g:
+        out = oracle.pointwise_fit_predict(spec, g['Xtr'], g['ytr'], g['Xq'])
+        _close(out, g['out'], rtol=2e-6, atol=1e-7)
+
+
+def test_pure_analog_k200(golden):
+    g = golden('pure_mean_analogs_k200')
+    o = oracle.pure_analog_predict(g['Xtr'][..., 0], g['ytr'][:, 0], g['Xq'][..., 0], 200, 'mean_analogs')
+    _close(o.astype(np.float32), g['out'][:, :, 0], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('name,k', [('analogreg_k10', 10), ('analogreg_k200', 200)])
+def test_analog_regression(golden, name, k):
+    g = golden(name)
+    for c in range(g['Xq'].shape[-1]):
+        o = oracle.analog_regression_predict(g['Xtr'][..., c], g['ytr'][:, c], g['Xq'][..., c], k)
+        _close(o, g['out64'][:, :, c], rtol=1e-9, atol=1e-10)
+    out = oracle.pointwise_fit_predict({'name': 'AnalogRegression', 'n_analogs': k}, g['Xtr'], g['ytr'], g['Xq'])
+    _close(out, g['out'], rtol=1e-5, atol=1e-6)
