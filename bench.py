@@ -1,0 +1,330 @@
+"""bench.py — headline benchmark: BcsdTemperature fit+predict throughput in cell-timesteps/s.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                       CPU arm (oracle port on host cores)
+
+Workload (BASELINE.json north_star / SURVEY.md §8(d)): the 720x1440 global 0.25-degree grid x
+10 950 daily steps, BcsdTemperature (monthly groups, return_anoms=True), float32 in / out.
+The full grid (4 arrays x 45.4 GB) does not fit one 180 GB GPU, so the per-GPU workload is
+the 8-GPU shard of that grid — 129 600 cells x 10 950 days — held FIXED as N grows (weak
+scaling; at N = 8 the job is exactly the headline configuration).  A step = one fit
+(two climatology kernels + the per-group sort) plus one predict over the shard, inputs
+resident in HBM.  Inputs (17 GB per GPU) are far larger than the 126 MB L2, so no flush is
+needed between steps.  Prints ONE JSON line (rank 0).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = 'cell_timesteps_per_sec_fit_predict_bcsd_temperature'
+UNIT = 'cell-timesteps/s'
+DAYS = 10950
+CELLS_PER_GPU = 129600           # 1/8 of 720 x 1440
+ALG_BYTES_STEP = 16              # read X_train, y_train, X_pred, write out (f32)
+ALG_BYTES_PREDICT = 8            # dominant kernel (qm_predict): read X_pred, write out
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--cells-per-gpu', type=int, default=CELLS_PER_GPU)
+    ap.add_argument('--days', type=int, default=DAYS)
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target CPU time of the cpu_baseline sample')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------- CPU arm
+def _oracle_cells(args):
+    """worker: oracle BcsdTemperature fit+predict on a block of cells (numpy port of the reference)."""
+    import oracle
+    import synth
+    T, c0, n, seed = args
+    idx = synth.daily_index(T)
+    Xtr, ytr, Xp = synth.temperature(T, n, seed=seed + c0)
+    t0 = time.perf_counter()
+    oracle.pointwise_fit_predict({'name': 'BcsdTemperature', 'return_anoms': True}, Xtr, ytr, Xp, idx, idx)
+    return time.perf_counter() - t0
+
+
+def cpu_sample(T: int, n_cells: int, cores: int):
+    """Time the oracle port on ``n_cells`` cells spread over ``cores`` worker processes."""
+    from joblib import Parallel, delayed
+    per = max(1, n_cells // cores)
+    jobs = [(T, i * per, per, 1000) for i in range(cores)]
+    t0 = time.perf_counter()
+    Parallel(n_jobs=cores)(delayed(_oracle_cells)(j) for j in jobs)
+    wall = time.perf_counter() - t0
+    done = per * cores
+    return done * T / wall, done, wall
+
+
+def cpu_baseline(T: int, target_seconds: float):
+    cores = os.cpu_count() or 1
+    _oracle_cells((T, 0, 1, 1))                         # import + warm-up
+    t1 = _oracle_cells((T, 0, 2, 1)) / 2                # seconds per cell per core
+    n_cells = int(max(cores, min(4096, cores * target_seconds / max(t1, 1e-4))))
+    value, done, wall = cpu_sample(T, n_cells, cores)
+    return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': f'oracle (numpy port of the reference algorithm) BcsdTemperature fit+predict on {done} cells x {T} days, '
+                      f'{cores} joblib processes, {wall:.1f} s wall'}
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The
+    Python reference cannot travel to the GPU box, so this is the oracle port (kind 'port')."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    _oracle_cells((a.days, 0, 1, 1))
+    t1 = _oracle_cells((a.days, 0, 2, 1)) / 2
+    budget = 120.0 / max(1, a.steps + a.warmup)        # keep the whole run within a few minutes
+    n_cells = int(max(cores, min(2048, cores * min(budget, 20.0) / max(t1, 1e-4))))
+    for _ in range(a.warmup):
+        cpu_sample(a.days, n_cells, cores)
+    vals, walls, done = [], [], 0
+    for _ in range(a.steps):
+        v, done, w = cpu_sample(a.days, n_cells, cores)
+        vals.append(v)
+        walls.append(w)
+    value = done * a.days * len(walls) / sum(walls)
+    sample = (f'oracle port, BcsdTemperature fit+predict, {done} cells x {a.days} days per step, '
+              f'{cores} joblib processes')
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': a.gpus,
+        'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': 1e3 * sum(walls) / len(walls),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 data, f64 keys/interp',
+        'data': 'synthetic',
+        'config': {'workload': f'BcsdTemperature fit+predict, monthly groups, {a.days} daily steps; bounded CPU sample of the '
+                               f'{a.cells_per_gpu}-cells-per-GPU shard of the 720x1440 grid', 'cells_per_step': done,
+                   'days': a.days},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 8 or not (t0 <= ts <= t1 + 0.2):
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)'
+    except Exception:
+        return 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    import skdownscale_b200  # noqa: F401
+    from skdownscale_b200 import _lib, engine
+    from skdownscale_b200.pointwise_models import BcsdTemperature, PointWiseDownscaler
+    import synth
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != a.gpus:
+        raise SystemExit(f'--gpus {a.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {a.gpus}')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()
+
+    T, C = a.days, a.cells_per_gpu
+    idx = synth.daily_index(T)
+    # synthetic temperature shard, generated on the device (SURVEY.md §8(d) formulas), seed + rank
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    season = torch.sin(2 * torch.pi * torch.arange(T, device=dev, dtype=torch.float32) / 365.25)[:, None]
+
+    def field(mean, amp, sd):
+        x = torch.randn((T, C), device=dev, dtype=torch.float32, generator=gen)
+        x.mul_(sd).add_(mean + amp * season)
+        return x
+
+    Xtr, ytr, Xp = field(15.0, 10.0, 3.0), field(14.0, 12.0, 2.0), field(16.5, 10.0, 3.0)
+    out = torch.empty((T, C), device=dev, dtype=torch.float32)
+    model = BcsdTemperature(return_anoms=True)
+
+    ev_pred = []
+
+    def step(time_predict=False):
+        model.fit_batched(Xtr, ytr, idx)
+        if time_predict:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        model.predict_batched(Xp, idx, out=out)
+        if time_predict:
+            e1.record()
+            ev_pred.append((e0, e1))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    t_wall0 = time.perf_counter()
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e_start.record()
+    for _ in range(a.steps):
+        step(time_predict=True)
+    e_stop.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms = torch.tensor([e_start.elapsed_time(e_stop)], device=dev, dtype=torch.float64)
+    pred_ms = torch.tensor([sum(x.elapsed_time(y) for x, y in ev_pred) / len(ev_pred)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pred_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    ms_total = float(ms.item())
+    ms_step = ms_total / a.steps
+    value = world * C * T / (ms_step * 1e-3)
+    model._state.check_finite()
+
+    # ---- end to end through the public API: pinned host inputs, H2D + fit + predict + D2H per step
+    e2e = None
+    if not a.no_e2e:
+        h = [torch.empty((T, C), dtype=torch.float32, pin_memory=True) for _ in range(4)]
+        for dst, src in zip(h[:3], (Xtr, ytr, Xp)):
+            dst.copy_(src)
+        torch.cuda.synchronize()
+        del Xtr, ytr, Xp, out
+        model._state = None
+        torch.cuda.empty_cache()
+        pw = PointWiseDownscaler(BcsdTemperature(return_anoms=True), device=dev)
+
+        def e2e_step():
+            pw.fit(h[0], h[1], time=idx)                 # H2D of X_train, y_train inside
+            res = pw.predict(h[2], time=idx)             # H2D of X_pred inside; result on the device
+            h[3].copy_(res, non_blocking=True)           # D2H of the predicted field
+            torch.cuda.synchronize()
+
+        e2e_step()                                       # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(a.e2e_steps):
+            e2e_step()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        tms = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e2e = {'value': world * C * T * a.e2e_steps / (float(tms.item()) * 1e-3), 'unit': UNIT,
+               'h2d_bytes_per_step': 3 * T * C * 4, 'd2h_bytes_per_step': T * C * 4, 'steps': a.e2e_steps,
+               'path': 'PointWiseDownscaler.fit(X, y) + .predict(X) on pinned host tensors, sequential H2D -> kernels -> D2H'}
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        pms = float(pred_ms.item())
+        ach = ALG_BYTES_PREDICT * C * T / (pms * 1e-3) / 1e9
+        ach_step = ALG_BYTES_STEP * C * T / (ms_step * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32 data, f64 keys/interp', 'data': 'synthetic',
+            'config': {'workload': f'BcsdTemperature fit+predict, monthly groups, return_anoms=True, {C} cells/GPU '
+                                   f'(the 8-GPU shard of the 720x1440 grid) x {T} daily steps, f32',
+                       'cells_per_gpu': C, 'days': T, 'parallelism': f'cells sharded over {world} GPU(s), no data-path collective',
+                       'l2': 'inputs 17 GB/GPU >> 126 MB L2 (no flush needed)'},
+            'clocks': clocks,
+            'e2e': e2e,
+            'gpu_launches': 4 * a.steps,
+            'roofline': {'bound': 'hbm', 'kernel': 'qm_predict_kernel (dominant)', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                         'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_cell_timestep': ALG_BYTES_PREDICT, 'kernel_ms': pms,
+                         'whole_step': {'achieved': ach_step, 'frac': ach_step / peak,
+                                        'algorithmic_bytes_per_cell_timestep': ALG_BYTES_STEP}},
+        }
+        if world == 1 and not a.no_cpu:
+            line['cpu_baseline'] = cpu_baseline(T, a.cpu_seconds)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)

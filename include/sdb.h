@@ -1,0 +1,156 @@
+/*
+ * sdb.h — C ABI of the B200-native pointwise statistical-downscaling engine.
+ *
+ * Drop-in boundary for the hot path of pangeo-data/scikit-downscale
+ * (`PointWiseDownscaler.fit/predict` over BcsdTemperature, BcsdPrecipitation,
+ * QuantileMapper, PureAnalog, AnalogRegression).  The reference has no native
+ * code: what these entry points replace is its per-cell Python loop
+ *   skdownscale/pointwise_models/core.py:69-97   (_fit_wrapper, one estimator.fit per cell)
+ *   skdownscale/pointwise_models/core.py:100-143 (_predict_wrapper, one estimator.predict per cell)
+ * together with the estimator bodies cited per function below.  A maintainer
+ * binds them from Python with ctypes.
+ *
+ * Conventions
+ *  - Every data pointer is a DEVICE pointer (cudaMalloc / torch CUDA tensor); the
+ *    caller owns all buffers; nothing is allocated inside.  `stream` is a
+ *    cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *    enqueue work; they do not synchronise.
+ *  - Arrays are "time-major, cell-fastest": element (t, c) of a [T, C] array is
+ *    at base[t * ld + c] (ld >= C, in elements) — the C-order (time, lat, lon)
+ *    layout of the reference's xarray inputs, zero-copy.  Multi-feature inputs
+ *    are [T, p, C]: element (t, f, c) at base[(t * p + f) * ld + c].
+ *  - dtype: SDB_F32 or SDB_F64 (inputs and fitted state share one dtype).
+ *  - Group tables (device, int32): rows[g * max_len + j] = row number (time
+ *    index) of the j-th member of group g in time order, -1 beyond len[g].
+ *  - cell_valid (device, uint8, may be NULL = all valid): 0 marks a cell the
+ *    reference would skip (core.py:35-37); its outputs are NaN.
+ *  - nonfinite (device, int32[1], may be NULL): the kernels OR 1 into it when they meet a
+ *    NaN/inf inside a valid cell — the condition on which the reference's sklearn
+ *    validation raises ValueError (base.py:18-20,29-31).  The caller zeroes it, reads
+ *    it back after synchronising and raises.
+ *  - Return value: 0 on success, negative on error (SDB_E_*); the message is
+ *    available from sdb_last_error() (thread-local).
+ *  - Thread safety: entry points keep no global mutable state apart from the
+ *    thread-local error string; distinct streams may be driven concurrently.
+ */
+#ifndef SDB_H_
+#define SDB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB_F32 0
+#define SDB_F64 1
+
+#define SDB_E_INVALID (-1)   /* bad argument (shape, dtype, NULL pointer, unsupported size) */
+#define SDB_E_CUDA    (-2)   /* CUDA launch / runtime error */
+#define SDB_E_UNSUPPORTED (-3)
+
+/* quantile-mapping predict modes */
+#define SDB_MODE_QM     0    /* QuantileMapper.transform        quantile.py:109-147 */
+#define SDB_MODE_BCSD_P 1    /* BcsdPrecipitation.predict       bcsd.py:149-185     */
+#define SDB_MODE_BCSD_T 2    /* BcsdTemperature.predict         bcsd.py:230-281     */
+
+/* group-mean arithmetic (what pandas does in the reference, see oracle/bcsd.py) */
+#define SDB_MEAN_GROUPBY 0   /* df.groupby().mean(): Kahan sum in input dtype   bcsd.py:138,222-223 */
+#define SDB_MEAN_FRAME   1   /* DataFrame.mean(): numpy pairwise sum            groupers.py:84-89   */
+
+/* PureAnalog kinds (gard.py:310-336) */
+#define SDB_ANALOG_BEST   0
+#define SDB_ANALOG_SAMPLE 1
+#define SDB_ANALOG_WEIGHT 2
+#define SDB_ANALOG_MEAN   3
+#define SDB_ANALOG_REGRESSION 4   /* AnalogRegression._predict_one_step  gard.py:191-224 */
+
+#define SDB_MAX_GROUP_LEN 16384   /* longest group (padded to a power of two) one CTA sorts */
+#define SDB_MAX_ANALOGS   256
+
+int sdb_version(void);
+const char* sdb_last_error(void);
+
+/* Largest group length supported by sdb_qm_fit / sdb_qm_predict. */
+int sdb_max_group_len(void);
+
+/*
+ * Per-group climatology of every cell: climo[g * ld_out + c] = mean of v over the rows
+ * of group g, in the arithmetic the reference's pandas call uses (`how`).
+ * Replaces  y_groups.mean() / X.groupby().mean()      bcsd.py:138, 222-223
+ *           PaddedDOYGrouper.mean()                    groupers.py:84-89
+ */
+int sdb_group_mean(const void* v, int dtype, int64_t ld, int64_t n_cells,
+                   const int32_t* rows, const int32_t* len, int n_groups, int max_len,
+                   int how, void* climo, int64_t ld_out,
+                   const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+/*
+ * Fit the empirical CDFs: for every cell and group, sort the group's values.
+ *   sorted_state[c * state_ld + state_off[g] + j] = j-th smallest value of group g in cell c
+ * Replaces  BcsdBase._qm_fit_by_group → QuantileMapper.fit → CunnaneTransformer.fit
+ *           bcsd.py:59-67, quantile.py:81-107, 438-463 (np.sort at :462).
+ * state_off: device int64[n_groups].
+ */
+int sdb_qm_fit(const void* y, int dtype, int64_t ld, int64_t n_cells,
+               const int32_t* rows, const int32_t* len, const int64_t* state_off,
+               int n_groups, int max_len,
+               void* sorted_state, int64_t state_ld,
+               const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+/*
+ * Quantile-map every cell and group of X through the fitted CDFs.
+ *   mode QM      out = QM_g(X)
+ *   mode BCSD_P  out = QM_g(X) [ / y_climo ]                         (return_anoms)
+ *   mode BCSD_T  roll = centred 9-sample mean inside the climate-trend group (float64),
+ *                shift = roll - x_climo, out = shift + QM_g(X - shift) [ - y_climo ]
+ * QM_g ranks the group's values among themselves (ties take the highest rank),
+ * converts ranks to Cunnane plotting positions and interpolates the fitted
+ * sorted values, with the reference's 10-endpoint OLS tails when T_pred > T_fit.
+ * Replaces  quantile.py:109-147, 465-545; bcsd.py:69-79, 149-185, 230-281.
+ *
+ * Predict group g uses fitted group state_gid[g] (device int32[n_groups]); fit_len /
+ * state_off (device, indexed by FITTED group) give its length and offset inside a cell's
+ * state record; x_climo / y_climo are [n_fit_groups, ld_climo] (may be NULL when unused).
+ * roll_nbr: NULL ⇒ the 9-sample window runs inside the predict group itself (monthly
+ * mode, bcsd.py:48-49); otherwise device int32[T_pred * 9] with the row numbers of the
+ * window members of every row (-1 = absent) — the general case where the climate-trend
+ * grouping differs from the mapping groups ('daily_nasa-nex', bcsd.py:53,250,275).
+ * rank_out: optional device int32 [T_pred, ld_out] receiving the 1-based in-group rank
+ * (parity instrumentation), or NULL.  out_dtype may differ from dtype (the reference's
+ * estimators return float64, its wrapper casts to X.dtype — core.py:129).
+ */
+int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, int64_t n_cells,
+                   const int32_t* rows, const int32_t* len, const int32_t* state_gid,
+                   int n_groups, int max_len,
+                   const int32_t* fit_len, const int64_t* state_off, int max_fit_len,
+                   const void* sorted_state, int64_t state_ld,
+                   const void* x_climo, const void* y_climo, int64_t ld_climo,
+                   int return_anoms, const int32_t* roll_nbr,
+                   void* out, int out_dtype, int64_t ld_out, int32_t* rank_out,
+                   const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+/*
+ * Analog downscaling for every cell: exact k-nearest-neighbour search of every query
+ * timestep in the cell's training window (float64 squared Euclidean distance,
+ * features accumulated in order, lowest index first on ties) followed by the
+ * PureAnalog statistic `kind` or the AnalogRegression OLS epilogue.
+ *   X_train [T_fit, p, C], y_train [T_fit, C], X_query [T_q, p, C]  (dtype)
+ *   out     [T_q, 3, C] (out_dtype): pred, exceedance_prob, prediction_error
+ *   knn_idx optional device int32 [T_q, k, C] (parity instrumentation) or NULL
+ *   rand_idx device int32 [T_q, C], only for SDB_ANALOG_SAMPLE (host-drawn, gard.py:315)
+ *   has_thresh/thresh: PureAnalog threshold masking (gard.py:303-308, 338-343)
+ * Replaces  AnalogBase.fit + PureAnalog.predict / AnalogRegression.predict
+ *           gard.py:58-87, 152-224, 273-364.
+ */
+int sdb_analog_predict(int kind, const void* X_train, const void* y_train, const void* X_query,
+                       int dtype, int64_t ld, int64_t n_cells,
+                       int t_fit, int t_query, int n_features, int k,
+                       int has_thresh, double thresh, const int32_t* rand_idx,
+                       void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
+                       const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB_H_ */

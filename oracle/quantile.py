@@ -40,7 +40,8 @@ def _ols_line(x: np.ndarray, y: np.ndarray) -> tuple[float, float]:
     xm = x.mean()
     ym = y.mean()
     dx = x - xm
-    slope = np.dot(dx, y - ym) / np.dot(dx, dx)
+    sxx = np.dot(dx, dx)
+    slope = np.dot(dx, y - ym) / sxx if sxx > 0 else 0.0     # single point: lstsq's minimum-norm answer
     return float(slope), float(ym - slope * xm)
 
 

@@ -1,0 +1,368 @@
+// analog_kernels.cu — GARD analog downscaling for every cell, sm_100a.
+//
+// Replaces, per cell and per query timestep,
+//   AnalogBase.fit (KDTree build)                  skdownscale/pointwise_models/gard.py:58-87
+//   PureAnalog.predict                              gard.py:273-364
+//   AnalogRegression.predict / _predict_one_step    gard.py:152-224 (thresh=None)
+// and the Python loop over cells around them (core.py:69-143).
+//
+// The k-nearest-neighbour search is an EXACT float64 brute force: squared Euclidean
+// distance accumulated feature by feature with separate multiply and add (-fmad=false),
+// which reproduces sklearn KDTree's neighbour indices bit for bit on tie-free data
+// (lowest train index first on exact ties).  One thread owns one query timestep and keeps
+// its running top-k; the CTA streams the cell's training window through shared memory
+// (float64, broadcast reads).  The work is FP64-pipe bound — there is no GEMM here (K = p
+// is 1..8 and the `|a|^2 - 2ab + |b|^2` trick would break index exactness), so no tensor
+// cores.
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cmath>
+
+#include "../../include/sdb.h"
+#include "common.cuh"
+
+namespace sdb {
+
+constexpr int AN_THREADS = 256;     // queries per CTA
+template <int P> struct AnChunk { static constexpr int value = (P <= 4) ? 1024 : 512; };   // training points staged per pass (<= 32 KB of float64)
+constexpr int AN_KREG = 16;         // top-k list kept in registers up to this k
+constexpr int AN_PMAX = 8;          // generic-feature kernel handles up to this many predictors
+
+struct AnalogParams {
+    const void* Xtr; const void* ytr; const void* Xq;
+    int64_t ld; int64_t C; int t_fit, t_query, p, k, kind;
+    int has_thresh; double thresh; const int32_t* rand_idx;
+    void* out; int out_f64; int64_t ld_out; int32_t* knn_idx;
+    const uint8_t* valid; int32_t* nonfinite;
+};
+
+__device__ __forceinline__ void store3(const AnalogParams& a, int q, int64_t c, double pred, double prob, double err) {
+    const int64_t base = (int64_t)q * 3 * a.ld_out + c;
+    if (a.out_f64) {
+        double* o = (double*)a.out;
+        o[base] = pred; o[base + a.ld_out] = prob; o[base + 2 * a.ld_out] = err;
+    } else {
+        float* o = (float*)a.out;
+        o[base] = (float)pred; o[base + a.ld_out] = (float)prob; o[base + 2 * a.ld_out] = (float)err;
+    }
+}
+
+// numpy pairwise summation of a small in-thread sequence (see qm_api.cu for the reference)
+template <typename F, typename Get>
+__device__ F np_pairwise(const Get& get, int lo, int n) {
+    if (n < 8) {
+        F res = (F)0;
+        for (int i = 0; i < n; ++i) res += get(lo + i);
+        return res;
+    } else if (n <= 128) {
+        F r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = get(lo + k);
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] += get(lo + i + k);
+        }
+        F res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; ++i) res += get(lo + i);
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return np_pairwise<F>(get, lo, n2) + np_pairwise<F>(get, lo + n2, n - n2);
+    }
+}
+// ndarray.sum along an axis: first element is the initial value, pairwise over the rest
+template <typename F, typename Get>
+__device__ F np_sum(const Get& get, int n) {
+    F s = get(0);
+    if (n > 1) s = s + np_pairwise<F>(get, 1, n - 1);
+    return s;
+}
+
+// ---- epilogues.  idx(i)/dist2(i): i-th nearest training row and its squared distance.
+template <typename T, typename IdxF, typename D2F>
+__device__ void pure_analog_epilogue(const AnalogParams& a, int q, int64_t c, int k, const IdxF& idx, const D2F& dist2) {
+    const T* y = (const T*)a.ytr;
+    auto yv = [&](int i) -> T { return y[(int64_t)idx(i) * a.ld + c]; };
+    const T th = (T)a.thresh;
+    int n_exceed = 0;
+    if (a.has_thresh) for (int i = 0; i < k; ++i) n_exceed += (yv(i) > th) ? 1 : 0;
+    const bool any_masked = a.has_thresh && (n_exceed < k);
+    double pred;
+    if (a.kind == SDB_ANALOG_BEST) {
+        pred = (double)yv(0);                                               // gard.py:310-311
+    } else if (a.kind == SDB_ANALOG_SAMPLE) {
+        pred = (double)yv(a.rand_idx[(int64_t)q * a.C + c]);               // gard.py:313-317
+    } else if (a.kind == SDB_ANALOG_WEIGHT) {                               // gard.py:319-327
+        if (any_masked) pred = NAN;
+        else {
+            auto w = [&](int i) -> double { double d = sqrt(dist2(i)); return 1.0 / (d == 0.0 ? 1e-20 : d); };
+            auto wy = [&](int i) -> double { return (double)yv(i) * w(i); };
+            const double scl = np_sum<double>(w, k);
+            pred = np_sum<double>(wy, k) / scl;
+        }
+    } else {                                                                // mean_analogs  gard.py:329-333
+        if (any_masked) pred = NAN;
+        else pred = (double)(np_sum<T>(yv, k) / (T)k);
+    }
+    double err, prob;
+    if (a.has_thresh) {                                                     // gard.py:338-343
+        if (pred != pred) pred = 0.0;                                       // nan_to_num
+        prob = (double)n_exceed / (double)k;
+    } else {
+        prob = 1.0;
+    }
+    if (any_masked) err = NAN;
+    else {                                                                  // ndarray.std, ddof=0, in y's dtype
+        const T mean = np_sum<T>(yv, k) / (T)k;
+        auto sq = [&](int i) -> T { T d = yv(i) - mean; return d * d; };
+        err = (double)(T)sqrt(np_sum<T>(sq, k) / (T)k);
+    }
+    store3(a, q, c, pred, prob, err);
+}
+
+// Ordinary least squares with intercept on the k analogs (sklearn LinearRegression:
+// centred least squares), prediction at the query point, in-sample RMSE.  gard.py:215-221
+template <typename T, int P, typename IdxF>
+__device__ void regression_epilogue(const AnalogParams& a, int q, int64_t c, int k, const IdxF& idx, const double (&xq)[P]) {
+    const T* X = (const T*)a.Xtr;
+    const T* y = (const T*)a.ytr;
+    const int p = (P == AN_PMAX) ? a.p : P;
+    auto xv = [&](int i, int f) -> double { return (double)X[((int64_t)idx(i) * a.p + f) * a.ld + c]; };
+    auto yv = [&](int i) -> double { return (double)y[(int64_t)idx(i) * a.ld + c]; };
+    double xm[P], ym = 0.0;
+#pragma unroll
+    for (int f = 0; f < P; ++f) xm[f] = 0.0;
+    for (int i = 0; i < k; ++i) {
+        ym += yv(i);
+#pragma unroll
+        for (int f = 0; f < P; ++f) if (f < p) xm[f] += xv(i, f);
+    }
+    ym /= (double)k;
+#pragma unroll
+    for (int f = 0; f < P; ++f) xm[f] /= (double)k;
+    // normal equations of the centred problem: A (p x p, symmetric) beta = b
+    double A[P][P], b[P];
+#pragma unroll
+    for (int f = 0; f < P; ++f) { b[f] = 0.0;
+#pragma unroll
+        for (int g = 0; g < P; ++g) A[f][g] = 0.0; }
+    for (int i = 0; i < k; ++i) {
+        double dx[P];
+#pragma unroll
+        for (int f = 0; f < P; ++f) dx[f] = (f < p) ? xv(i, f) - xm[f] : 0.0;
+        const double dy = yv(i) - ym;
+#pragma unroll
+        for (int f = 0; f < P; ++f) { b[f] += dx[f] * dy;
+#pragma unroll
+            for (int g = 0; g <= f; ++g) A[f][g] += dx[f] * dx[g]; }
+    }
+    // Cholesky A = L L^T (lower, in place); a zero pivot (degenerate analog cloud) drops that
+    // direction, i.e. a minimum-norm-like solution with beta_f = 0.
+    double beta[P];
+    bool live[P];
+#pragma unroll
+    for (int f = 0; f < P; ++f) {
+        live[f] = f < p;
+#pragma unroll
+        for (int g = 0; g <= f; ++g) {
+            double s = A[f][g];
+#pragma unroll
+            for (int h = 0; h < g; ++h) s -= A[f][h] * A[g][h];
+            if (g == f) {
+                if (!(s > 1e-300) || !live[f]) { live[f] = false; A[f][f] = 1.0; }
+                else A[f][f] = sqrt(s);
+            } else {
+                A[f][g] = live[g] ? s / A[g][g] : 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < P; ++f) {                      // forward substitution
+        double s = b[f];
+#pragma unroll
+        for (int h = 0; h < f; ++h) s -= A[f][h] * beta[h];
+        beta[f] = live[f] ? s / A[f][f] : 0.0;
+    }
+#pragma unroll
+    for (int f = P - 1; f >= 0; --f) {                 // back substitution
+        double s = beta[f];
+#pragma unroll
+        for (int h = f + 1; h < P; ++h) s -= A[h][f] * beta[h];
+        beta[f] = live[f] ? s / A[f][f] : 0.0;
+    }
+    double icpt = ym;
+#pragma unroll
+    for (int f = 0; f < P; ++f) icpt -= xm[f] * beta[f];
+    double sse = 0.0;
+    for (int i = 0; i < k; ++i) {
+        double yh = icpt;
+#pragma unroll
+        for (int f = 0; f < P; ++f) if (f < p) yh += xv(i, f) * beta[f];
+        const double r = yv(i) - yh;
+        sse += r * r;
+    }
+    double pred = icpt;
+#pragma unroll
+    for (int f = 0; f < P; ++f) if (f < p) pred += xq[f] * beta[f];
+    store3(a, q, c, pred, 1.0, sqrt(sse / (double)k));
+}
+
+// ---- the search kernel
+template <typename T, int P, int KREG>
+__global__ void __launch_bounds__(AN_THREADS)
+analog_kernel(const AnalogParams a) {
+    constexpr int AN_CHUNK = AnChunk<P>::value;
+    __shared__ double chunk[AN_CHUNK * P];
+    const int n_tiles = (a.t_query + AN_THREADS - 1) / AN_THREADS;
+    const int64_t c = blockIdx.x / n_tiles;           // consecutive CTAs share a cell: its window stays in L2
+    const int tile = blockIdx.x - (int)(c * n_tiles);
+    if (a.valid && !a.valid[c]) {
+        const int q = tile * AN_THREADS + threadIdx.x;
+        if (q < a.t_query) store3(a, q, c, NAN, NAN, NAN);
+        return;
+    }
+    const int p = (P == AN_PMAX) ? a.p : P;
+    const int k = a.k;
+    const T* Xtr = (const T*)a.Xtr;
+    const T* Xq = (const T*)a.Xq;
+    const int q = tile * AN_THREADS + threadIdx.x;
+    const bool live = q < a.t_query;
+    double xq[P];
+#pragma unroll
+    for (int f = 0; f < P; ++f) {
+        xq[f] = (live && f < p) ? (double)Xq[((int64_t)q * a.p + f) * a.ld + c] : 0.0;
+        if (live && f < p && a.nonfinite && !isfinite(xq[f])) atomicOr(a.nonfinite, 1);
+    }
+    // running top-k, ascending by (distance, index)
+    constexpr int KL = (KREG > 0) ? KREG : SDB_MAX_ANALOGS;
+    double bd[KL];
+    int bi[KL];
+#pragma unroll
+    for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) { bd[i] = INFINITY; bi[i] = -1; }
+    if (KREG == 0) for (int i = 0; i < k; ++i) { bd[i] = INFINITY; bi[i] = -1; }
+    double worst = INFINITY;                          // current k-th best distance
+
+    for (int t0 = 0; t0 < a.t_fit; t0 += AN_CHUNK) {
+        const int nt = min(AN_CHUNK, a.t_fit - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt * p; i += AN_THREADS) {
+            const int t = i / p, f = i - t * p;
+            const double xv = (double)Xtr[((int64_t)(t0 + t) * a.p + f) * a.ld + c];
+            if (a.nonfinite && tile == 0 && !isfinite(xv)) atomicOr(a.nonfinite, 1);
+            chunk[t * P + f] = xv;
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int t = 0; t < nt; ++t) {
+            double d = 0.0;
+#pragma unroll
+            for (int f = 0; f < P; ++f) {
+                if (f < p) { const double tmp = xq[f] - chunk[t * P + f]; d += tmp * tmp; }
+            }
+            if (d < worst) {
+                const int id = t0 + t;
+                if (KREG > 0) {
+                    // branch-free insertion into the register list (strict < keeps the earlier index first on ties)
+#pragma unroll
+                    for (int i = KREG - 1; i > 0; --i) {
+                        const bool shift = d < bd[i - 1];
+                        const bool here = !shift && (d < bd[i]);
+                        const double nd = shift ? bd[i - 1] : (here ? d : bd[i]);
+                        const int ni = shift ? bi[i - 1] : (here ? id : bi[i]);
+                        bd[i] = nd; bi[i] = ni;
+                    }
+                    if (d < bd[0]) { bd[0] = d; bi[0] = id; }
+                    // k may be smaller than KREG: the k-th entry is the acceptance bound
+                    double w = bd[KREG - 1];
+#pragma unroll
+                    for (int i = 0; i < KREG; ++i) if (i == k - 1) w = bd[i];
+                    worst = w;
+                } else {
+                    int i = k - 1;
+                    while (i > 0 && d < bd[i - 1]) { bd[i] = bd[i - 1]; bi[i] = bi[i - 1]; --i; }
+                    bd[i] = d; bi[i] = id;
+                    worst = bd[k - 1];
+                }
+            }
+        }
+    }
+    if (!live) return;
+    if (a.knn_idx) {
+        if (KREG > 0) {
+#pragma unroll
+            for (int i = 0; i < KREG; ++i) if (i < k) a.knn_idx[((int64_t)q * k + i) * a.C + c] = bi[i];
+        } else {
+            for (int i = 0; i < k; ++i) a.knn_idx[((int64_t)q * k + i) * a.C + c] = bi[i];
+        }
+    }
+    if constexpr (KREG > 0) {
+        // park the winners in local arrays the epilogues can index dynamically (the search
+        // list itself stays in registers)
+        int li[KREG]; double ld2[KREG];
+#pragma unroll
+        for (int i = 0; i < KREG; ++i) { li[i] = bi[i]; ld2[i] = bd[i]; }
+        auto idx = [&](int i) -> int { return li[i]; };
+        auto dist2 = [&](int i) -> double { return ld2[i]; };
+        if (a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<T, P>(a, q, c, k, idx, xq);
+        else pure_analog_epilogue<T>(a, q, c, k, idx, dist2);
+    } else {
+        auto idx = [&](int i) -> int { return bi[i]; };
+        auto dist2 = [&](int i) -> double { return bd[i]; };
+        if (a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<T, P>(a, q, c, k, idx, xq);
+        else pure_analog_epilogue<T>(a, q, c, k, idx, dist2);
+    }
+}
+
+template <typename T, int P>
+static int launch_analog(const AnalogParams& a, cudaStream_t st) {
+    const int64_t n_tiles = (a.t_query + AN_THREADS - 1) / AN_THREADS;
+    if (n_tiles * a.C > 2147483647LL) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_analog_predict: too many (cell, query tile) pairs for one launch; split the shard");
+    dim3 grid((unsigned)(n_tiles * a.C));
+    if (a.k <= AN_KREG) analog_kernel<T, P, AN_KREG><<<grid, AN_THREADS, 0, st>>>(a);
+    else                analog_kernel<T, P, 0><<<grid, AN_THREADS, 0, st>>>(a);
+    SDB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+static int dispatch_analog(const AnalogParams& a, cudaStream_t st) {
+    switch (a.p) {
+        case 1: return launch_analog<T, 1>(a, st);
+        case 2: return launch_analog<T, 2>(a, st);
+        case 3: return launch_analog<T, 3>(a, st);
+        case 4: return launch_analog<T, 4>(a, st);
+        default: return launch_analog<T, AN_PMAX>(a, st);
+    }
+}
+
+}  // namespace sdb
+
+using namespace sdb;
+
+extern "C" int sdb_analog_predict(int kind, const void* X_train, const void* y_train, const void* X_query,
+                                  int dtype, int64_t ld, int64_t n_cells,
+                                  int t_fit, int t_query, int n_features, int k,
+                                  int has_thresh, double thresh, const int32_t* rand_idx,
+                                  void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
+                                  const uint8_t* cell_valid, int32_t* nonfinite, void* stream) {
+    if (!X_train || !y_train || !X_query || !out) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: NULL pointer");
+    if (n_cells <= 0 || t_fit <= 0 || t_query <= 0 || ld < n_cells || ld_out < n_cells)
+        return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: bad shape");
+    if (n_features < 1 || n_features > AN_PMAX) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_analog_predict: 1..%d predictors supported, got %d", AN_PMAX, n_features);
+    if (k < 1 || k > SDB_MAX_ANALOGS || k > t_fit) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: k=%d out of range (1..min(%d, T_fit))", k, SDB_MAX_ANALOGS);
+    if (kind < SDB_ANALOG_BEST || kind > SDB_ANALOG_REGRESSION) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: unknown kind %d", kind);
+    if (kind == SDB_ANALOG_SAMPLE && !rand_idx) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: sample_analogs needs rand_idx");
+    if (kind == SDB_ANALOG_REGRESSION && has_thresh) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_analog_predict: AnalogRegression(thresh=...) is not implemented");
+    if ((dtype != SDB_F32 && dtype != SDB_F64) || (out_dtype != SDB_F32 && out_dtype != SDB_F64))
+        return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: bad dtype");
+    AnalogParams a;
+    a.Xtr = X_train; a.ytr = y_train; a.Xq = X_query; a.ld = ld; a.C = n_cells;
+    a.t_fit = t_fit; a.t_query = t_query; a.p = n_features; a.k = k; a.kind = kind;
+    a.has_thresh = has_thresh; a.thresh = thresh; a.rand_idx = rand_idx;
+    a.out = out; a.out_f64 = (out_dtype == SDB_F64); a.ld_out = ld_out; a.knn_idx = knn_idx;
+    a.valid = cell_valid; a.nonfinite = nonfinite;
+    cudaStream_t st = (cudaStream_t)stream;
+    return dtype == SDB_F32 ? dispatch_analog<float>(a, st) : dispatch_analog<double>(a, st);
+}

@@ -1,0 +1,248 @@
+"""Batched host-side dispatcher: builds the (tiny, exact, integer) group tables on the host,
+owns the device-resident fitted state, and calls the CUDA kernels through the C ABI
+(``include/sdb.h``) once per (fit | predict) for ALL cells of a device shard.
+
+This replaces the reference's two Python loops over cells
+(skdownscale/pointwise_models/core.py:86-96 and :137-141) and everything they call per
+cell.  torch is used only for device memory and streams.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_TORCH_CODE = {torch.float32: _lib.SDB_F32, torch.float64: _lib.SDB_F64}
+
+
+def _code(t: torch.Tensor) -> int:
+    try:
+        return _TORCH_CODE[t.dtype]
+    except KeyError:
+        raise TypeError(f'only float32 / float64 are supported on the device path, got {t.dtype}') from None
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_2d(t: torch.Tensor, name: str) -> int:
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor (skdownscale_b200 has no CPU path)')
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f'{name} must be [time, cell] with the cell axis contiguous, got shape '
+                         f'{tuple(t.shape)} strides {t.stride()}')
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+def as_device(a, device, dtype=None) -> torch.Tensor:
+    """numpy / torch → CUDA tensor (the H2D copy of the public API)."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        a = np.asarray(a)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=True)
+
+
+class GroupTable:
+    """A set of time groups: ``rows[g, j]`` = row number of the j-th member of group g in the
+    order the reference would hand them to numpy, ``-1`` beyond ``len[g]``.  Built on the host
+    (exact integer work, done once per call — the reference redoes it per cell)."""
+
+    def __init__(self, groups):
+        groups = [(k, np.asarray(r, dtype=np.int64)) for k, r in groups]
+        self.keys = [k for k, _ in groups]
+        self.key_to_gid = {k: i for i, k in enumerate(self.keys)}
+        self.len = np.array([len(r) for _, r in groups], dtype=np.int32)
+        self.max_len = int(self.len.max()) if len(groups) else 0
+        self.n_groups = len(groups)
+        self.rows = np.full((self.n_groups, max(self.max_len, 1)), -1, dtype=np.int32)
+        for i, (_, r) in enumerate(groups):
+            self.rows[i, :len(r)] = r
+        self._dev = {}
+
+    def subset(self, gids) -> 'GroupTable':
+        return GroupTable([(self.keys[g], self.rows[g, :self.len[g]]) for g in gids])
+
+    def device(self, device):
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = (torch.from_numpy(self.rows).to(device), torch.from_numpy(self.len).to(device))
+        return self._dev[key]
+
+
+@dataclass
+class QMFitted:
+    """Fitted empirical CDFs + climatologies of every cell of a device shard."""
+    dtype: torch.dtype
+    n_cells: int
+    sort_table: GroupTable                 # groups whose sorted values are held
+    state_off: np.ndarray                  # int64 [n sorted groups], offset inside a cell record
+    state_ld: int
+    sorted_state: torch.Tensor             # [C, state_ld]
+    fit_len_dev: torch.Tensor
+    state_off_dev: torch.Tensor
+    mean_table: GroupTable | None = None   # groups of the climatologies (superset of sort_table keys)
+    x_climo: torch.Tensor | None = None    # [n mean groups, C]
+    y_climo: torch.Tensor | None = None
+    valid: torch.Tensor | None = None      # uint8 [C]
+    nonfinite: torch.Tensor | None = None  # int32 [1]
+    extra: dict = field(default_factory=dict)
+
+    def check_finite(self):
+        """Raise like the reference's sklearn validation (base.py:18-20) if a kernel met NaN/inf."""
+        if self.nonfinite is not None and int(self.nonfinite.item()) != 0:
+            self.nonfinite.zero_()
+            raise ValueError('Input contains NaN or infinity.')
+
+
+def cell_mask(first_row: torch.Tensor) -> torch.Tensor:
+    """core.py:35-37: a cell takes part iff its first timestep (first feature) is not NaN."""
+    return (~torch.isnan(first_row)).to(torch.uint8).contiguous()
+
+
+def group_mean(v: torch.Tensor, table: GroupTable, how: int, valid=None, nonfinite=None) -> torch.Tensor:
+    lib = _lib.load()
+    ld = _check_2d(v, 'v')
+    C = v.shape[1]
+    rows, length = table.device(v.device)
+    out = torch.empty((table.n_groups, C), dtype=v.dtype, device=v.device)
+    _lib.check(lib.sdb_group_mean(_ptr(v), _code(v), ld, C, _ptr(rows), _ptr(length), table.n_groups,
+                                  table.rows.shape[1], how, _ptr(out), C, _ptr(valid), _ptr(nonfinite),
+                                  _stream()), 'sdb_group_mean')
+    return out
+
+
+def qm_fit(y: torch.Tensor, sort_table: GroupTable, *, valid=None, X=None, mean_table=None,
+           mean_how: int = _lib.MEAN_GROUPBY, want_y_climo: bool = True) -> QMFitted:
+    """fit: sort every (cell, group) of ``y`` and compute the climatologies.
+
+    BcsdTemperature.fit / BcsdPrecipitation.fit / QuantileMapper.fit for all cells
+    (bcsd.py:115-147, 197-228; quantile.py:81-107)."""
+    lib = _lib.load()
+    ld = _check_2d(y, 'y')
+    T, C = y.shape
+    if sort_table.max_len > lib.sdb_max_group_len():
+        raise NotImplementedError(f'time groups longer than {lib.sdb_max_group_len()} steps are not supported yet '
+                                  f'(got {sort_table.max_len})')
+    lens = sort_table.len.astype(np.int64)
+    padded = (lens + 3) // 4 * 4                       # keep every group 16-byte aligned inside a record
+    off = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
+    state_ld = int(padded.sum())
+    dev = y.device
+    state = torch.empty((C, state_ld), dtype=y.dtype, device=dev)
+    off_dev = torch.from_numpy(off).to(dev)
+    rows, length = sort_table.device(dev)
+    nonfinite = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(lib.sdb_qm_fit(_ptr(y), _code(y), ld, C, _ptr(rows), _ptr(length), _ptr(off_dev),
+                              sort_table.n_groups, sort_table.rows.shape[1], _ptr(state), state_ld,
+                              _ptr(valid), _ptr(nonfinite), _stream()), 'sdb_qm_fit')
+    st = QMFitted(dtype=y.dtype, n_cells=C, sort_table=sort_table, state_off=off, state_ld=state_ld,
+                  sorted_state=state, fit_len_dev=length, state_off_dev=off_dev, valid=valid,
+                  nonfinite=nonfinite)
+    mt = mean_table if mean_table is not None else sort_table
+    st.mean_table = mt
+    if want_y_climo:
+        st.y_climo = group_mean(y, mt, mean_how, valid, nonfinite)
+    if X is not None:
+        if X.shape != y.shape:
+            raise ValueError(f'X {tuple(X.shape)} and y {tuple(y.shape)} must have the same shape')
+        st.x_climo = group_mean(X, mt, mean_how, valid, nonfinite)
+    return st
+
+
+def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, return_anoms: bool = False,
+               roll_nbr: np.ndarray | None = None, out_dtype=None, want_rank: bool = False, out=None,
+               climo_gid: np.ndarray | None = None):
+    """predict: quantile-map every (cell, group) of ``X`` through the fitted CDFs.
+
+    ``table`` = mapping groups of the prediction index; group g uses the fitted group with
+    the same key (``KeyError`` like the reference's dict / ``.loc`` lookup otherwise)."""
+    lib = _lib.load()
+    ld = _check_2d(X, 'X')
+    T, C = X.shape
+    if C != st.n_cells:
+        raise ValueError(f'X has {C} cells, the model was fitted on {st.n_cells}')
+    if X.dtype != st.dtype:
+        raise TypeError(f'X is {X.dtype}, the model was fitted on {st.dtype}')
+    if table.max_len > lib.sdb_max_group_len():
+        raise NotImplementedError(f'time groups longer than {lib.sdb_max_group_len()} steps are not supported yet')
+    dev = X.device
+    try:
+        gid = np.array([st.sort_table.key_to_gid[k] for k in table.keys], dtype=np.int32)
+    except KeyError as e:
+        raise KeyError(e.args[0]) from None
+    # climatologies are indexed by the MEAN table; re-index them by sorted group when they differ
+    x_climo, y_climo = st.x_climo, st.y_climo
+    if st.mean_table is not st.sort_table and (x_climo is not None or y_climo is not None):
+        sel = torch.as_tensor([st.mean_table.key_to_gid[k] for k in st.sort_table.keys], device=dev)
+        key = 'climo_by_sort'
+        if key not in st.extra:
+            st.extra[key] = (None if x_climo is None else x_climo.index_select(0, sel).contiguous(),
+                             None if y_climo is None else y_climo.index_select(0, sel).contiguous())
+        x_climo, y_climo = st.extra[key]
+    gid_dev = torch.from_numpy(gid).to(dev)
+    rows, length = table.device(dev)
+    od = out_dtype or X.dtype
+    if out is None:
+        out = torch.empty((T, C), dtype=od, device=dev)
+    ld_out = _check_2d(out, 'out')
+    rank = torch.zeros((T, C), dtype=torch.int32, device=dev) if want_rank else None
+    if rank is not None and ld_out != C:
+        raise ValueError('want_rank needs a contiguous output')
+    nbr_dev = None
+    if roll_nbr is not None:
+        nbr_dev = torch.from_numpy(np.ascontiguousarray(roll_nbr, dtype=np.int32)).to(dev)
+    _lib.check(lib.sdb_qm_predict(mode, _ptr(X), _code(X), ld, C,
+                                  _ptr(rows), _ptr(length), _ptr(gid_dev), table.n_groups, table.rows.shape[1],
+                                  _ptr(st.fit_len_dev), _ptr(st.state_off_dev), st.sort_table.max_len,
+                                  _ptr(st.sorted_state), st.state_ld,
+                                  _ptr(x_climo), _ptr(y_climo), C,
+                                  int(bool(return_anoms)), _ptr(nbr_dev),
+                                  _ptr(out), _TORCH_CODE[out.dtype], ld_out, _ptr(rank),
+                                  _ptr(st.valid), _ptr(st.nonfinite), _stream()), 'sdb_qm_predict')
+    return (out, rank) if want_rank else out
+
+
+def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_query: torch.Tensor, k: int, *,
+                   thresh=None, rand_idx=None, out_dtype=None, want_idx: bool = False, valid=None,
+                   nonfinite=None):
+    """PureAnalog / AnalogRegression fit+predict for all cells (gard.py:58-87, 152-224, 273-364).
+
+    X_train [T, p, C], y_train [T, C], X_query [Tq, p, C] → out [Tq, 3, C]."""
+    lib = _lib.load()
+    for name, t in (('X_train', X_train), ('y_train', y_train), ('X_query', X_query)):
+        if not t.is_cuda:
+            raise RuntimeError(f'{name} must be a CUDA tensor (skdownscale_b200 has no CPU path)')
+    X_train = X_train.contiguous()
+    X_query = X_query.contiguous()
+    y_train = y_train.contiguous()
+    T, p, C = X_train.shape
+    Tq = X_query.shape[0]
+    if X_query.shape[1:] != (p, C) or y_train.shape != (T, C):
+        raise ValueError('shape mismatch between X_train, y_train and X_query')
+    if X_query.dtype != X_train.dtype or y_train.dtype != X_train.dtype:
+        raise TypeError('X_train, y_train and X_query must share one dtype')
+    dev = X_train.device
+    od = out_dtype or X_train.dtype
+    out = torch.empty((Tq, 3, C), dtype=od, device=dev)
+    idx = torch.empty((Tq, k, C), dtype=torch.int32, device=dev) if want_idx else None
+    if rand_idx is not None:
+        rand_idx = torch.as_tensor(np.ascontiguousarray(rand_idx, dtype=np.int32)).to(dev)
+    _lib.check(lib.sdb_analog_predict(kind, _ptr(X_train), _ptr(y_train), _ptr(X_query), _code(X_train), C, C,
+                                      T, Tq, p, k, int(thresh is not None),
+                                      float(thresh) if thresh is not None else 0.0, _ptr(rand_idx),
+                                      _ptr(out), _TORCH_CODE[od], C, _ptr(idx), _ptr(valid), _ptr(nonfinite),
+                                      _stream()), 'sdb_analog_predict')
+    return (out, idx) if want_idx else out

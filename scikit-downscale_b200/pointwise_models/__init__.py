@@ -1,0 +1,22 @@
+"""Drop-in surface of ``skdownscale.pointwise_models`` for the B200 hot path
+(skdownscale/pointwise_models/__init__.py:1-36).  Estimators outside the hot path
+(PureRegression, ZScoreRegressor, EquidistantCdfMatcher, ...) are not provided.
+"""
+
+from .bcsd import BcsdPrecipitation, BcsdTemperature
+from .core import PointWiseDownscaler
+from .gard import AnalogRegression, PureAnalog
+from .groupers import DAY_GROUPER, MONTH_GROUPER, PaddedDOYGrouper
+from .quantile import QuantileMapper
+
+__all__ = [
+    'BcsdPrecipitation',
+    'BcsdTemperature',
+    'PointWiseDownscaler',
+    'AnalogRegression',
+    'PureAnalog',
+    'DAY_GROUPER',
+    'MONTH_GROUPER',
+    'PaddedDOYGrouper',
+    'QuantileMapper',
+]

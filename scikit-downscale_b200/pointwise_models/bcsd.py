@@ -1,0 +1,164 @@
+"""BcsdTemperature / BcsdPrecipitation — drop-ins for
+skdownscale/pointwise_models/bcsd.py:14-289, executed for all cells at once on the GPU.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+import torch
+from sklearn.exceptions import NotFittedError
+
+from .. import _lib, engine
+from .base import TimeSynchronousDownscaler, cuda_device, series_to_device
+from .groupers import (DAY_GROUPER, MONTH_GROUPER, PaddedDOYGrouper, grouper_keys, groups_from_keys,
+                       padded_doy_groups, rolling_neighbours)
+from .quantile import check_qt_kwargs
+from .utils import default_none_kwargs
+
+
+class BcsdBase(TimeSynchronousDownscaler):
+    """Base class for BCSD model (bcsd.py:14-93)."""
+
+    _fit_attributes = ['y_climo_', 'quantile_mappers_']
+    _timestep = 'M'
+    _mode = None
+    _needs_x_climo = False
+
+    def __init__(self, time_grouper=MONTH_GROUPER, climate_trend_grouper=DAY_GROUPER,
+                 climate_trend=MONTH_GROUPER, return_anoms=True, qm_kwargs=None):
+        self.time_grouper = time_grouper
+        self.climate_trend_grouper = climate_trend_grouper
+        self.climate_trend = climate_trend
+        self.return_anoms = return_anoms
+        self.qm_kwargs = qm_kwargs
+
+    def _pre_fit(self):
+        """bcsd.py:34-44, including the in-place replacement of the constructor argument by the
+        grouper class that the reference's own test asserts (test_pointwise_models.py:315-320)."""
+        if isinstance(self.time_grouper, str):
+            if self.time_grouper == 'daily_nasa-nex':
+                self.time_grouper = PaddedDOYGrouper
+                self.timestep = 'daily'
+            else:
+                raise NotImplementedError(f"time_grouper={self.time_grouper!r}: only callables and "
+                                          "'daily_nasa-nex' run on the B200 path")
+        elif self.time_grouper is PaddedDOYGrouper:
+            self.timestep = 'daily'
+        else:
+            self.time_grouper_ = self.time_grouper
+            self.timestep = 'monthly'
+        qm = default_none_kwargs(self.qm_kwargs)
+        for k in qm:
+            if k not in ('detrend', 'lt_kwargs', 'qt_kwargs'):
+                raise TypeError(f"QuantileMapper.__init__() got an unexpected keyword argument '{k}'")
+        if qm.get('detrend', False):
+            raise NotImplementedError('qm_kwargs detrend=True is not on the B200 path yet')
+        check_qt_kwargs(qm.get('qt_kwargs'))
+
+    # ------------------------------------------------------------------ group tables (host, exact)
+    def _fit_tables(self, index):
+        if self.timestep == 'monthly':
+            t = engine.GroupTable(groups_from_keys(grouper_keys(self.time_grouper, index)))
+            return t, t, _lib.MEAN_GROUPBY
+        full = engine.GroupTable(padded_doy_groups(index))
+        # predict only ever looks up day-of-month keys 1..31 (bcsd.py:53,275): sort those groups,
+        # keep the climatology of all 366
+        return full.subset(range(31)), full, _lib.MEAN_FRAME
+
+    def _predict_tables(self, index):
+        """(mapping groups, neighbour table or None)."""
+        if self.timestep == 'monthly':
+            qm_keys = grouper_keys(self.time_grouper, index)
+        else:
+            qm_keys = grouper_keys(self.climate_trend_grouper, index)
+        table = engine.GroupTable(groups_from_keys(qm_keys))
+        nbr = None
+        if self._mode == _lib.MODE_BCSD_T:
+            roll_keys = grouper_keys(self.climate_trend, index)
+            if not np.array_equal(np.asarray(roll_keys), np.asarray(qm_keys)):
+                nbr = rolling_neighbours(groups_from_keys(roll_keys), len(index))
+        return table, nbr
+
+    # ------------------------------------------------------------------ batched API
+    def fit_batched(self, X: torch.Tensor, y: torch.Tensor, index, valid=None):
+        """fit for all cells: X, y ``[T, C]`` CUDA tensors sharing the time ``index``."""
+        self._pre_fit()
+        sort_t, mean_t, how = self._fit_tables(index)
+        self._state = engine.qm_fit(y, sort_t, valid=valid, X=X if self._needs_x_climo else None,
+                                    mean_table=mean_t, mean_how=how)
+        self.n_features_in_ = 1
+        return self
+
+    def check_fit(self):
+        """Deferred (synchronising) checks of fit: NaN/inf inputs (base.py:18-20) and the
+        precipitation climatology (bcsd.py:140-141)."""
+        self._state.check_finite()
+
+    def predict_batched(self, X: torch.Tensor, index, out_dtype=None, want_rank=False, out=None):
+        if not hasattr(self, '_state'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
+                                 "appropriate arguments before using this estimator.")
+        if self.timestep == 'daily' and self.return_anoms:
+            # bcsd.py:267,271-281 / 170-185: the padded groups overlap, the regrouped frame has a
+            # different shape and the reference raises
+            raise ValueError('shape of climo is not equal to input array')
+        table, nbr = self._predict_tables(index)
+        return engine.qm_predict(self._state, X, table, self._mode, return_anoms=self.return_anoms,
+                                 roll_nbr=nbr, out_dtype=out_dtype, want_rank=want_rank, out=out)
+
+    # ------------------------------------------------------------------ per-cell API of the reference
+    def fit(self, X, y):
+        X, y = self._frames(X, y)
+        dev = cuda_device()
+        x_t, index, _ = series_to_device(X, dev)
+        y_t, _, _ = series_to_device(y, dev)
+        if x_t.shape[1] != 1:
+            raise ValueError(f'BCSD only supports 1 feature, found {x_t.shape[1]}')
+        if y_t.shape[1] != 1:
+            raise ValueError('y must have exactly one column')
+        if x_t.dtype != y_t.dtype:
+            x_t, y_t = x_t.to(torch.float64), y_t.to(torch.float64)
+        self.fit_batched(x_t, y_t, index)
+        self.check_fit()
+        self.y_climo_ = pd.DataFrame(self._state.y_climo.cpu().numpy(), index=self._state.mean_table.keys)
+        if self._state.x_climo is not None:
+            self._x_climo = pd.DataFrame(self._state.x_climo.cpu().numpy(), index=self._state.mean_table.keys)
+        return self
+
+    def predict(self, X):
+        if not hasattr(self, '_state'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
+                                 "appropriate arguments before using this estimator.")
+        X = self._frames(X)
+        x_t, index, columns = series_to_device(X, cuda_device())
+        if x_t.shape[1] != self.n_features_in_:
+            raise ValueError(f'X has {x_t.shape[1]} features, but {self.__class__.__name__} was fitted with '
+                             f'{self.n_features_in_} features.')
+        if x_t.dtype != self._state.dtype:
+            x_t = x_t.to(self._state.dtype)
+        out = self.predict_batched(x_t, index, out_dtype=torch.float64)
+        self._state.check_finite()
+        return pd.DataFrame(out.cpu().numpy(), index=index, columns=columns)
+
+
+class BcsdPrecipitation(BcsdBase):
+    """Classic BCSD model for precipitation (bcsd.py:96-193)."""
+
+    _mode = _lib.MODE_BCSD_P
+    _needs_x_climo = False
+
+    def check_fit(self):
+        super().check_fit()
+        st = self._state
+        if self.return_anoms:                                   # bcsd.py:140-141
+            yc = st.y_climo if st.valid is None else st.y_climo[:, st.valid.bool()]
+            if yc.numel() and bool((yc <= 0).any().item()):
+                raise ValueError('Invalid value in target climatology')
+
+
+class BcsdTemperature(BcsdBase):
+    """Classic BCSD model for temperature (bcsd.py:196-289)."""
+
+    _mode = _lib.MODE_BCSD_T
+    _needs_x_climo = True

@@ -1,0 +1,334 @@
+"""GPU parity tests: the CUDA path (through the C ABI / ctypes) against
+
+* the golden vectors produced by the LIVE reference (tests/golden/), and
+* the numpy oracle on seeded inputs (in-group ranks and analog indices BIT-EXACT, values
+  within the north-star tolerance 1e-5 relative: |a-b| <= 1e-5 * max(|b|, sigma_y)),
+* size-independent properties at larger sizes.
+
+Run on the B200 box with ``pytest -m gpu``.  Nothing here reads /root/reference.
+"""
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+import oracle
+import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5      # north_star: mapped floating values within 1e-5 relative
+
+
+@pytest.fixture(scope='module')
+def dev():
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    import skdownscale_b200  # noqa: F401
+    return torch.device('cuda:0')
+
+
+def pm():
+    import skdownscale_b200.pointwise_models as m
+    return m
+
+
+def eng():
+    from skdownscale_b200 import engine
+    return engine
+
+
+def assert_close(got, ref, scale=1.0, rtol=RTOL):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    nan_g, nan_r = np.isnan(got), np.isnan(ref)
+    assert np.array_equal(nan_g, nan_r), 'NaN pattern differs'
+    tol = rtol * np.maximum(np.abs(ref), scale)
+    bad = np.abs(got - ref) > tol
+    bad &= ~nan_r
+    assert not bad.any(), f'{bad.sum()} / {bad.size} outside tolerance, max abs err {np.nanmax(np.abs(got - ref))}'
+
+
+# ------------------------------------------------------------------ QuantileMapper
+def test_qm_known_answer(dev, golden):
+    g = golden('qm_known_answer')      # reference test_pointwise_models.py:81-90
+    mapper = pm().QuantileMapper().fit(g['fit'])
+    actual = mapper.transform(g['x'])
+    assert actual.shape == (100, 1) and actual.dtype == np.float64
+    np.testing.assert_almost_equal(actual, g['fit'])
+    np.testing.assert_allclose(actual, g['out'], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize('name', ['qm_equal_len', 'qm_pred_longer', 'qm_pred_shorter', 'qm_ties', 'qm_f64', 'qm_tiny'])
+def test_qm_golden(dev, golden, name):
+    g = golden(name)
+    pw = pm().PointWiseDownscaler(pm().QuantileMapper())
+    pw.fit(g['ytr'])
+    got = pw.transform(g['Xp'])
+    assert got.dtype == g['Xp'].dtype
+    assert_close(got, g['out'].astype(g['Xp'].dtype), scale=np.std(g['ytr']))
+    # float64 result of the per-cell API: the only difference left is summation order in the tails
+    for c in range(g['Xp'].shape[1]):
+        m = pm().QuantileMapper().fit(g['ytr'][:, c:c + 1])
+        o = m.transform(g['Xp'][:, c:c + 1])[:, 0]
+        np.testing.assert_allclose(o, g['out'][:, c], rtol=1e-11, atol=1e-11)
+
+
+@pytest.mark.parametrize('n_fit,n_pred', [(1, 1), (2, 5), (255, 256), (256, 256), (257, 257), (1024, 1024),
+                                          (1025, 1000), (4096, 4096), (4097, 5000), (10950, 10950), (16384, 16384)])
+def test_qm_sizes_vs_oracle(dev, n_fit, n_pred):
+    """every padded-size boundary of the sorting network; ranks bit-exact, values 1e-5."""
+    C = 5
+    rng = np.random.default_rng(n_fit * 31 + n_pred)
+    y = rng.standard_normal((n_fit, C)).astype(np.float32) * 5 + 3
+    x = rng.standard_normal((n_pred, C)).astype(np.float32) * 6 + 4
+    x[: n_pred // 3, 0] = x[0, 0]                  # a long run of exact ties in cell 0
+    m = pm().QuantileMapper()
+    m.fit_batched(eng().as_device(y, dev))
+    out, rank = m.transform_batched(eng().as_device(x, dev), out_dtype=torch.float64, want_rank=True)
+    out, rank = out.cpu().numpy(), rank.cpu().numpy()
+    for c in range(C):
+        st = oracle.quantile_mapper_fit(y[:, c])
+        o, r = oracle.quantile_mapper_transform(x[:, c], st, return_rank=True)
+        assert np.array_equal(rank[:, c], r), f'rank mismatch in cell {c}'
+        np.testing.assert_allclose(out[:, c], o, rtol=1e-10, atol=1e-10)
+
+
+def test_qm_group_too_long(dev):
+    y = torch.zeros((16385, 2), device=dev)
+    with pytest.raises(NotImplementedError):
+        pm().QuantileMapper().fit_batched(y)
+
+
+def test_qm_sorted_multiset_property(dev):
+    """n == m, tie-free: the mapped series of every cell is a permutation of the fitted one,
+    arranged in the rank order of the input (size-independent property, larger shape)."""
+    T, C = 10950, 512
+    gen = torch.Generator(device=dev).manual_seed(0)
+    y = torch.randn((T, C), device=dev, generator=gen)
+    x = torch.randn((T, C), device=dev, generator=gen) * 2 + 1
+    m = pm().QuantileMapper()
+    m.fit_batched(y)
+    out = m.transform_batched(x)
+    torch.testing.assert_close(torch.sort(out, dim=0).values, torch.sort(y, dim=0).values, rtol=0, atol=0)
+    torch.testing.assert_close(torch.argsort(out, dim=0), torch.argsort(x, dim=0), rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------ BCSD
+@pytest.mark.parametrize('name,kw', [
+    ('bcsd_t_month_anoms', {}),
+    ('bcsd_t_month_abs', {'return_anoms': False}),
+    ('bcsd_t_month_future', {}),
+    ('bcsd_t_month_f64', {}),
+    ('bcsd_t_month_30yr', {}),
+    ('bcsd_t_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
+])
+def test_bcsd_temperature_golden(dev, golden, name, kw):
+    g = golden(name)
+    idx_f = synth.daily_index(len(g['Xtr']), str(g['start_fit']))
+    idx_p = synth.daily_index(len(g['Xp']), str(g['start_pred']))
+    pw = pm().PointWiseDownscaler(pm().BcsdTemperature(**kw))
+    pw.fit(g['Xtr'], g['ytr'], time=idx_f)
+    got = pw.predict(g['Xp'], time=idx_p)
+    assert got.dtype == g['Xp'].dtype and got.shape == g['out'].shape
+    assert_close(got, g['out'], scale=np.nanstd(g['ytr']))
+    # per-cell estimator API (config[0] of BASELINE.json): float64 DataFrame like the reference
+    c = 0
+    m = pm().BcsdTemperature(**kw)
+    m.fit(pd.DataFrame({'x': g['Xtr'][:, c]}, index=idx_f), pd.DataFrame({'x': g['ytr'][:, c]}, index=idx_f))
+    o = m.predict(pd.DataFrame({'x': g['Xp'][:, c]}, index=idx_p))
+    assert isinstance(o, pd.DataFrame) and o.shape == (len(idx_p), 1) and o.values.dtype == np.float64
+    assert o.index.equals(idx_p)
+    np.testing.assert_allclose(o.values[:, 0], g['out64'][:, c], rtol=0, atol=2e-6 * np.nanstd(g['ytr']))
+
+
+@pytest.mark.parametrize('name,kw', [
+    ('bcsd_p_month_anoms', {}),
+    ('bcsd_p_month_abs_future', {'return_anoms': False}),
+    ('bcsd_p_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
+])
+def test_bcsd_precipitation_golden(dev, golden, name, kw):
+    g = golden(name)
+    idx_f = synth.daily_index(len(g['Xtr']), str(g['start_fit']))
+    idx_p = synth.daily_index(len(g['Xp']), str(g['start_pred']))
+    pw = pm().PointWiseDownscaler(pm().BcsdPrecipitation(**kw))
+    pw.fit(g['Xtr'], g['ytr'], time=idx_f)
+    got = pw.predict(g['Xp'], time=idx_p)
+    assert_close(got, g['out'], scale=np.std(g['ytr']))
+
+
+def test_bcsd_errors(dev):
+    idx = synth.daily_index(800)
+    z = np.zeros((800, 3), np.float32)
+    pw = pm().PointWiseDownscaler(pm().BcsdPrecipitation())
+    with pytest.raises(ValueError, match='Invalid value in target climatology'):      # bcsd.py:140-141
+        pw.fit(z + 1, z, time=idx)
+    Xtr, ytr, Xp = synth.temperature(800, 3, 5)
+    bad = ytr.copy()
+    bad[100, 1] = np.nan                                                               # NaN inside an unmasked cell
+    pw = pm().PointWiseDownscaler(pm().BcsdTemperature())
+    with pytest.raises(ValueError, match='NaN'):                                       # base.py:18-20
+        pw.fit(Xtr, bad, time=idx)
+    m = pm().BcsdTemperature(time_grouper='daily_nasa-nex')                            # return_anoms=True
+    pw = pm().PointWiseDownscaler(m)
+    pw.fit(Xtr, ytr, time=idx)
+    with pytest.raises(ValueError, match='shape of climo'):                            # bcsd.py:267,279-280
+        pw.predict(Xp, time=idx)
+    with pytest.raises(ValueError, match='1 feature'):
+        pm().BcsdTemperature().fit(pd.DataFrame(np.zeros((10, 2)), index=idx[:10]), pd.DataFrame(np.zeros((10, 1)), index=idx[:10]))
+    with pytest.raises(AssertionError):                                                # base.py:17
+        pm().BcsdTemperature().fit(pd.DataFrame(np.zeros((10, 1)), index=idx[:10]), pd.DataFrame(np.zeros((10, 1)), index=idx[5:15]))
+
+
+@pytest.mark.parametrize('anoms', [True, False])
+def test_bcsd_temperature_vs_oracle_ranks(dev, anoms):
+    """30-year daily series, ragged cell count, NaN cells; ranks bit-exact, values 1e-5."""
+    T, C = 10950, 37
+    idx = synth.daily_index(T)
+    Xtr, ytr, Xp = synth.temperature(T, C, seed=3)
+    for c in (4, 36):
+        Xtr[:, c] = np.nan
+    m = pm().BcsdTemperature(return_anoms=anoms)
+    xtr = eng().as_device(Xtr, dev)
+    m.fit_batched(xtr, eng().as_device(ytr, dev), idx, valid=eng().cell_mask(xtr[0]))
+    out, rank = m.predict_batched(eng().as_device(Xp, dev), idx, want_rank=True)
+    out, rank = out.cpu().numpy(), rank.cpu().numpy()
+    groups = oracle.groups_from_keys(oracle.month_keys(idx))
+    for c in range(0, C, 3):
+        if np.isnan(Xtr[0, c]):
+            assert np.isnan(out[:, c]).all()
+            continue
+        st = oracle.bcsd_temperature_fit(Xtr[:, c], ytr[:, c], groups)
+        o, r = oracle.bcsd_temperature_predict(st, Xp[:, c], groups, groups, anoms, return_rank=True)
+        assert np.array_equal(rank[:, c], r), f'rank mismatch cell {c}'
+        assert_close(out[:, c], o.astype(np.float32), scale=np.std(ytr[:, c]))
+    assert np.isnan(out[:, 4]).all() and np.isnan(out[:, 36]).all()
+    # fitted climatologies are the reference's float32 Kahan means, bit for bit
+    yc = m._state.y_climo.cpu().numpy()
+    for gi, (key, rows) in enumerate(groups):
+        assert yc[gi, 0] == oracle.bcsd._group_mean_like_pandas(ytr[rows, 0])
+
+
+def test_bcsd_precipitation_vs_oracle(dev):
+    T, C = 3653, 16
+    idx = synth.daily_index(T)
+    Xtr, ytr, Xp = synth.precipitation(T, C, seed=9)
+    m = pm().BcsdPrecipitation()
+    m.fit_batched(eng().as_device(Xtr, dev), eng().as_device(ytr, dev), idx)
+    m.check_fit()
+    out, rank = m.predict_batched(eng().as_device(Xp, dev), idx, want_rank=True)
+    out, rank = out.cpu().numpy(), rank.cpu().numpy()
+    groups = oracle.groups_from_keys(oracle.month_keys(idx))
+    for c in range(C):
+        st = oracle.bcsd_precipitation_fit(ytr[:, c], groups)
+        o, r = oracle.bcsd_precipitation_predict(st, Xp[:, c], groups, True, return_rank=True)
+        assert np.array_equal(rank[:, c], r)          # all zeros of a group share the highest rank
+        assert_close(out[:, c], o.astype(np.float32), scale=1.0)
+
+
+def test_bcsd_custom_grouper_and_strided_views(dev):
+    """callable grouper (quarters) + inputs that are column slices of a wider array (ld > C)."""
+    T, C = 2000, 12
+    idx = synth.daily_index(T)
+    Xtr, ytr, Xp = synth.temperature(T, C + 5, seed=11)
+    q = lambda ts: ts.quarter   # noqa: E731
+    m = pm().BcsdTemperature(time_grouper=q, climate_trend=q)
+    d = lambda a: eng().as_device(a, dev)[:, 2:2 + C]   # noqa: E731
+    m.fit_batched(d(Xtr), d(ytr), idx)
+    out = m.predict_batched(d(Xp), idx).cpu().numpy()
+    groups = oracle.groups_from_keys(np.asarray(idx.quarter))
+    for c in (0, C - 1):
+        st = oracle.bcsd_temperature_fit(Xtr[:, 2 + c], ytr[:, 2 + c], groups)
+        o = oracle.bcsd_temperature_predict(st, Xp[:, 2 + c], groups, groups, True)
+        assert_close(out[:, c], o.astype(np.float32), scale=np.std(ytr))
+    # climate_trend left at MONTH while mapping by quarter → neighbour-table kernel
+    m2 = pm().BcsdTemperature(time_grouper=q)
+    m2.fit_batched(d(Xtr), d(ytr), idx)
+    out2 = m2.predict_batched(d(Xp), idx).cpu().numpy()
+    roll = oracle.groups_from_keys(oracle.month_keys(idx))
+    st = oracle.bcsd_temperature_fit(Xtr[:, 2], ytr[:, 2], groups)
+    o2 = oracle.bcsd_temperature_predict(st, Xp[:, 2], roll, groups, True)
+    assert_close(out2[:, 0], o2.astype(np.float32), scale=np.std(ytr))
+
+
+def test_bcsd_abs_multiset_property(dev):
+    """return_anoms=False, same index: (out - shift) of every month group is a permutation of the
+    fitted y of that group — checked via sums on a larger block (size-independent)."""
+    T, C = 10950, 1024
+    idx = synth.daily_index(T)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    s = torch.sin(2 * torch.pi * torch.arange(T, device=dev) / 365.25)[:, None]
+    Xtr = 15 + 10 * s + 3 * torch.randn((T, C), device=dev, generator=gen)
+    ytr = 14 + 12 * s + 2 * torch.randn((T, C), device=dev, generator=gen)
+    m = pm().BcsdPrecipitation(return_anoms=False)      # pure per-month QM of X onto y's distribution
+    m.fit_batched(Xtr, ytr, idx)
+    out = m.predict_batched(Xtr, idx)
+    month = torch.as_tensor(np.asarray(idx.month), device=dev)
+    for mo in (1, 2, 7, 12):
+        sel = month == mo
+        torch.testing.assert_close(torch.sort(out[sel], dim=0).values, torch.sort(ytr[sel], dim=0).values, rtol=0, atol=0)
+
+
+# ------------------------------------------------------------------ GARD
+@pytest.mark.parametrize('kind', ['best_analog', 'mean_analogs', 'weight_analogs', 'sample_analogs'])
+@pytest.mark.parametrize('suffix,thresh', [('', None), ('_thresh', 0.0)])
+def test_pure_analog_golden(dev, golden, kind, suffix, thresh):
+    g = golden(f'pure_{kind}{suffix}')
+    model = pm().PureAnalog(n_analogs=10, kind=kind, thresh=thresh)
+    pw = pm().PointWiseDownscaler(model)
+    pw.fit(g['Xtr'], g['ytr'])
+    if kind == 'sample_analogs':
+        np.random.seed(1234)                     # same global-RNG stream as the reference run (gard.py:315)
+    got = pw.predict(g['Xq'])
+    assert got.shape == g['out'].shape and got.dtype == g['Xq'].dtype
+    assert_close(got, g['out'], scale=np.std(g['ytr']))
+
+
+def test_pure_analog_k200_golden(dev, golden):
+    g = golden('pure_mean_analogs_k200')
+    pw = pm().PointWiseDownscaler(pm().PureAnalog(n_analogs=200, kind='mean_analogs'))
+    pw.fit(g['Xtr'], g['ytr'])
+    assert_close(pw.predict(g['Xq']), g['out'], scale=np.std(g['ytr']))
+
+
+@pytest.mark.parametrize('name,k', [('analogreg_k10', 10), ('analogreg_k200', 200)])
+def test_analog_regression_golden(dev, golden, name, k):
+    g = golden(name)
+    pw = pm().PointWiseDownscaler(pm().AnalogRegression(n_analogs=k))
+    pw.fit(g['Xtr'], g['ytr'])
+    got = pw.predict(g['Xq'])
+    assert_close(got, g['out'], scale=np.std(g['ytr']))
+    # per-cell estimator API, float64
+    m = pm().AnalogRegression(n_analogs=k).fit(pd.DataFrame(g['Xtr'][..., 0]), pd.DataFrame(g['ytr'][:, 0]))
+    o = m.predict(pd.DataFrame(g['Xq'][..., 0]))
+    assert list(o.columns) == ['pred', 'exceedance_prob', 'prediction_error']
+    np.testing.assert_allclose(o.values, g['out64'][:, :, 0], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize('p,k,T,Tq', [(1, 5, 700, 300), (3, 10, 2500, 600), (3, 16, 1100, 257), (3, 17, 900, 100),
+                                      (4, 10, 1030, 90), (6, 8, 600, 70), (3, 200, 1500, 64)])
+def test_analog_indices_bit_exact(dev, p, k, T, Tq):
+    """kNN indices against the float64 brute-force oracle: bit-exact, every k / p code path."""
+    C = 3
+    Xtr, ytr, Xq = synth.analog(T, Tq, C, p, seed=100 + p + k)
+    m = pm().AnalogRegression(n_analogs=k)
+    m.fit_batched(eng().as_device(Xtr, dev), eng().as_device(ytr, dev))
+    out, idx = m.predict_batched(eng().as_device(Xq, dev), out_dtype=torch.float64, want_idx=True)
+    out, idx = out.cpu().numpy(), idx.cpu().numpy()
+    for c in range(C):
+        o, inds = oracle.analog_regression_predict(Xtr[..., c], ytr[:, c], Xq[..., c], k, return_inds=True)
+        assert np.array_equal(idx[:, :, c], inds), f'kNN index mismatch cell {c}'
+        np.testing.assert_allclose(out[:, :, c], o, rtol=1e-7, atol=1e-8)
+
+
+def test_analog_masked_cells_and_small_train(dev):
+    Xtr, ytr, Xq = synth.analog(6, 20, 4, 3, seed=5)
+    Xtr[:, :, 2] = np.nan
+    pw = pm().PointWiseDownscaler(pm().PureAnalog(n_analogs=10, kind='mean_analogs'))
+    with pytest.warns(UserWarning, match='less than n_analogs'):      # gard.py:75-79
+        pw.fit(Xtr, ytr)
+    got = pw.predict(Xq)
+    assert np.isnan(got[:, :, 2]).all()
+    ref = oracle.pointwise_fit_predict({'name': 'PureAnalog', 'n_analogs': 10, 'kind': 'mean_analogs'}, Xtr, ytr, Xq)
+    assert_close(got, ref, scale=1.0)

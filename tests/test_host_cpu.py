@@ -1,0 +1,113 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol that
+include/sdb.h declares, the group tables match the oracle, and the product refuses to run
+without CUDA (no CPU fallback)."""
+
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import oracle
+import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    import __graft_entry__ as ge
+    from skdownscale_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        ge.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from skdownscale_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'sdb.h')).read()
+    declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(sdb_\w+)\s*\(', hdr, flags=re.M))
+    assert declared == set(_lib.SIGNATURES), (declared, set(_lib.SIGNATURES))
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.sdb_version() >= 100
+    assert lib.sdb_max_group_len() == 16384
+
+
+def test_abi_rejects_bad_arguments(lib):
+    from skdownscale_b200 import _lib
+    rc = lib.sdb_qm_fit(None, 0, 1, 1, None, None, None, 1, 1, None, 1, None, None, None)
+    assert rc == -1 and b'NULL' in lib.sdb_last_error()
+    with pytest.raises(_lib.SdbError):
+        _lib.check(rc, 'sdb_qm_fit')
+
+
+def test_group_tables_match_oracle():
+    from skdownscale_b200.pointwise_models import groupers as g
+    idx = synth.daily_index(10950)
+    a = g.groups_from_keys(g.grouper_keys(g.MONTH_GROUPER, idx))
+    b = oracle.groups_from_keys(oracle.month_keys(idx))
+    assert [k for k, _ in a] == [k for k, _ in b]
+    for (_, ra), (_, rb) in zip(a, b):
+        np.testing.assert_array_equal(ra, rb)
+    assert max(len(r) for _, r in a) == 930 and min(len(r) for _, r in a) == 847
+    # arbitrary callable grouper goes through Index.map like df.groupby(callable)
+    c = g.groups_from_keys(g.grouper_keys(lambda ts: ts.quarter, idx))
+    assert [k for k, _ in c] == [1, 2, 3, 4]
+    d = g.padded_doy_groups(idx)
+    e = oracle.padded_doy_groups(idx)
+    for (ka, ra), (kb, rb) in zip(d, e):
+        assert ka == kb
+        np.testing.assert_array_equal(ra, rb)
+
+
+def test_padded_doy_grouper_class(golden):
+    from skdownscale_b200.pointwise_models import PaddedDOYGrouper
+    index = pd.date_range(start='1980-01-01', end='1982-12-31')
+    X = pd.DataFrame({'foo': np.arange(len(index), dtype=np.float64)}, index=index)
+    groups = dict(list(PaddedDOYGrouper(X)))          # skdownscale/test/test_pointwise_models.py:302-312
+    np.testing.assert_array_equal(np.unique(groups[123].index.dayofyear), np.arange(108, 139))
+    gref = golden('padded_doy_1980_1982')
+    for d in (1, 60, 123, 365, 366):
+        np.testing.assert_array_equal(groups[d]['foo'].values.astype(int), gref['rows'][d - 1][:gref['lens'][d - 1]])
+    assert PaddedDOYGrouper(X).mean().shape == (366, 1)
+
+
+def test_rolling_neighbours():
+    from skdownscale_b200.pointwise_models import groupers as g
+    idx = synth.daily_index(800)
+    groups = g.groups_from_keys(g.grouper_keys(g.MONTH_GROUPER, idx))
+    nbr = g.rolling_neighbours(groups, 800)
+    x = np.random.default_rng(0).standard_normal(800)
+    for _, rows in groups:
+        want = oracle.bcsd.rolling9_centered(x[rows])
+        got = np.array([x[nbr[r][nbr[r] >= 0]].mean() for r in rows])
+        np.testing.assert_allclose(got, want, rtol=1e-13)
+
+
+def test_estimator_surface_and_no_cpu_fallback():
+    import torch
+    from skdownscale_b200.pointwise_models import (AnalogRegression, BcsdPrecipitation, BcsdTemperature,
+                                                   PointWiseDownscaler, PureAnalog, QuantileMapper)
+    from sklearn.base import clone
+    m = BcsdTemperature(return_anoms=False)
+    assert clone(m).get_params()['return_anoms'] is False
+    assert PureAnalog.n_outputs == 3 and AnalogRegression.output_names == ['pred', 'exceedance_prob', 'prediction_error']
+    with pytest.raises(TypeError):
+        PointWiseDownscaler(object())                  # core.py:220-223
+    pw = PointWiseDownscaler(BcsdPrecipitation())
+    with pytest.raises(ValueError):
+        pw.fit(np.zeros((4, 2)), np.zeros((4, 2)), np.zeros((4, 2)))   # core.py:249-250
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            pw.fit(np.zeros((40, 2), np.float32), np.zeros((40, 2), np.float32), time=synth.daily_index(40))
+        with pytest.raises(RuntimeError, match='no CPU fallback'):
+            QuantileMapper().fit(np.zeros((10, 1)))
+    # _pre_fit replaces the constructor argument by the grouper class (test_pointwise_models.py:315-320)
+    from skdownscale_b200.pointwise_models import PaddedDOYGrouper
+    m = BcsdTemperature(time_grouper='daily_nasa-nex', return_anoms=False)
+    m._pre_fit()
+    assert issubclass(m.time_grouper, PaddedDOYGrouper)
+    with pytest.raises(NotImplementedError):
+        QuantileMapper(detrend=True).fit_batched(None)
