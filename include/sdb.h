@@ -71,6 +71,10 @@ extern "C" {
 int sdb_version(void);
 const char* sdb_last_error(void);
 
+/* Testing aid: bit 0 forces the generic (any dtype / any group length) kernels even where the
+ * float32 tile kernels apply.  Returns the previous flags. */
+int sdb_set_debug_flags(int flags);
+
 /* Largest group length supported by sdb_qm_fit / sdb_qm_predict. */
 int sdb_max_group_len(void);
 

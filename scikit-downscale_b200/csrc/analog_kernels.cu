@@ -20,6 +20,7 @@
 
 #include "../../include/sdb.h"
 #include "common.cuh"
+#include "np_pairwise.cuh"
 
 namespace sdb {
 
@@ -45,39 +46,6 @@ __device__ __forceinline__ void store3(const AnalogParams& a, int q, int64_t c, 
         float* o = (float*)a.out;
         o[base] = (float)pred; o[base + a.ld_out] = (float)prob; o[base + 2 * a.ld_out] = (float)err;
     }
-}
-
-// numpy pairwise summation of a small in-thread sequence (see qm_api.cu for the reference)
-template <typename F, typename Get>
-__device__ F np_pairwise(const Get& get, int lo, int n) {
-    if (n < 8) {
-        F res = (F)0;
-        for (int i = 0; i < n; ++i) res += get(lo + i);
-        return res;
-    } else if (n <= 128) {
-        F r[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = get(lo + k);
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] += get(lo + i + k);
-        }
-        F res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += get(lo + i);
-        return res;
-    } else {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        return np_pairwise<F>(get, lo, n2) + np_pairwise<F>(get, lo + n2, n - n2);
-    }
-}
-// ndarray.sum along an axis: first element is the initial value, pairwise over the rest
-template <typename F, typename Get>
-__device__ F np_sum(const Get& get, int n) {
-    F s = get(0);
-    if (n > 1) s = s + np_pairwise<F>(get, 1, n - 1);
-    return s;
 }
 
 // ---- epilogues.  idx(i)/dist2(i): i-th nearest training row and its squared distance.

@@ -1,5 +1,6 @@
 // qm_api.cu — extern "C" entry points of the quantile-mapping path (include/sdb.h).
 #include "qm_kernels.cuh"
+#include "np_pairwise.cuh"
 
 namespace sdb {
 
@@ -9,33 +10,6 @@ struct RowReader {
     const T* v; int64_t ld; int64_t c; const int32_t* rg;
     __device__ __forceinline__ T operator()(int j) const { return v[(int64_t)rg[j] * ld + c]; }
 };
-
-// numpy's pairwise summation (numpy/_core/src/umath/loops_utils.h.src, *_pairwise_sum), the
-// arithmetic behind DataFrame.mean() → nanops.nanmean → ndarray.sum (groupers.py:84-89).
-template <typename T>
-__device__ T np_pairwise_sum(const RowReader<T>& a, int lo, int n) {
-    if (n < 8) {
-        T res = (T)0;
-        for (int i = 0; i < n; ++i) res += a(lo + i);
-        return res;
-    } else if (n <= 128) {
-        T r[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) r[k] = a(lo + k);
-        int i;
-        for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] += a(lo + i + k);
-        }
-        T res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-        for (; i < n; ++i) res += a(lo + i);
-        return res;
-    } else {
-        int n2 = n / 2;
-        n2 -= n2 % 8;
-        return np_pairwise_sum(a, lo, n2) + np_pairwise_sum(a, lo + n2, n - n2);
-    }
-}
 
 template <typename T>
 __global__ void group_mean_kernel(const T* __restrict__ v, int64_t ld, int64_t C,
@@ -66,7 +40,7 @@ __global__ void group_mean_kernel(const T* __restrict__ v, int64_t ld, int64_t C
     } else {
         // ndarray.sum: first element copied as the initial value, pairwise over the rest
         T s = a(0);
-        if (n > 1) s = s + np_pairwise_sum(a, 1, n - 1);
+        if (n > 1) s = s + np_pairwise<T>(a, 1, n - 1);
         flag_nonfinite(s, nonfinite);
         *dst = s / (T)n;
     }
@@ -81,9 +55,13 @@ static int pick_np(int max_len) {
     return -1;
 }
 
+static int g_debug_flags = 0;      // bit 0: force the generic kernels (testing)
+
 }  // namespace sdb
 
 using namespace sdb;
+
+extern "C" int sdb_set_debug_flags(int flags) { int old = g_debug_flags; g_debug_flags = flags; return old; }
 
 extern "C" int sdb_max_group_len(void) { return SDB_MAX_GROUP_LEN; }
 
@@ -116,6 +94,10 @@ extern "C" int sdb_qm_fit(const void* y, int dtype, int64_t ld, int64_t n_cells,
     if (dtype != SDB_F32 && dtype != SDB_F64) return sdb_fail(SDB_E_INVALID, "sdb_qm_fit: bad dtype %d", dtype);
     FitParams f{y, ld, n_cells, rows, len, state_off, n_groups, max_len, sorted_state, state_ld, cell_valid, nonfinite};
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SDB_F32 && !(g_debug_flags & 1)) {
+        if (max_len <= 256) return qm_fit_tile_np256(f, st);
+        if (max_len <= 1024) return qm_fit_tile_np1024(f, st);
+    }
     switch (pick_np(max_len)) {
         case 256:   return qm_fit_np256(dtype, f, st);
         case 1024:  return qm_fit_np1024(dtype, f, st);
@@ -153,6 +135,11 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
     p.mode = mode; p.out_f64 = (out_dtype == SDB_F64); p.n_groups = n_groups;
     const int kind = (mode != SDB_MODE_BCSD_T) ? KIND_RAW : (roll_nbr ? KIND_SHIFT_TAB : KIND_SHIFT);
     cudaStream_t st = (cudaStream_t)stream;
+    const int longest = max_len > max_fit_len ? max_len : max_fit_len;
+    if (dtype == SDB_F32 && out_dtype == SDB_F32 && kind != KIND_SHIFT_TAB && longest <= 1024 && !(g_debug_flags & 1)) {
+        if (longest <= 256) return qm_predict_tile_np256(kind, p, st);
+        return qm_predict_tile_np1024(kind, p, st);
+    }
     switch (pick_np(max_len)) {
         case 256:   return qm_predict_np256(dtype, kind, p, st);
         case 1024:  return qm_predict_np1024(dtype, kind, p, st);

@@ -135,42 +135,49 @@ __device__ __forceinline__ double pp_of(int i, double den) { return ((double)i -
 
 // OLS line through `ne` (pp, value) points starting at 1-based index i0 (quantile.py:532-543;
 // sklearn LinearRegression = centred least squares; slope 0 when the abscissae coincide,
-// which is the minimum-norm lstsq answer for a single point).
-template <typename T>
-__device__ void ols_tail(const T* S, int i0, int ne, double den, double& slope, double& icpt) {
+// which is the minimum-norm lstsq answer for a single point).  S(i): 0-based sorted value.
+template <class Acc>
+__device__ void ols_tail(const Acc& S, int i0, int ne, double den, double& slope, double& icpt) {
     double xm = 0.0, ym = 0.0;
-    for (int k = 0; k < ne; ++k) { xm += pp_of(i0 + k, den); ym += (double)S[i0 - 1 + k]; }
+    for (int k = 0; k < ne; ++k) { xm += pp_of(i0 + k, den); ym += S(i0 - 1 + k); }
     xm /= (double)ne; ym /= (double)ne;
     double sxy = 0.0, sxx = 0.0;
     for (int k = 0; k < ne; ++k) {
         double dx = pp_of(i0 + k, den) - xm;
-        sxy += dx * ((double)S[i0 - 1 + k] - ym);
+        sxy += dx * (S(i0 - 1 + k) - ym);
         sxx += dx * dx;
     }
     slope = (sxx > 0.0) ? sxy / sxx : 0.0;
     icpt = ym - slope * xm;
 }
 
-// inverse CDF: value of the fitted sorted series S (length m) at the quantile of rank r of n
-// (CunnaneTransformer.inverse_transform, quantile.py:523-545 = np.interp + OLS tails)
-template <typename T>
-__device__ double inverse_cdf(int r, int n, int m, const T* __restrict__ S, double dn, double dm) {
-    if (n == m) return (double)S[r - 1];             // q lands exactly on knot r: np.interp returns fp[r-1]
+// inverse CDF: value of the fitted sorted series S (length m, accessor returning double) at the
+// quantile of rank r of n (CunnaneTransformer.inverse_transform, quantile.py:523-545 =
+// np.interp + OLS tails)
+template <class Acc>
+__device__ double inverse_cdf_acc(int r, int n, int m, const Acc& S, double dn, double dm) {
+    if (n == m) return S(r - 1);                     // q lands exactly on knot r: np.interp returns fp[r-1]
     const double q = pp_of(r, dn);
     const double p1 = pp_of(1, dm), pm = pp_of(m, dm);
     const int ne = m < 10 ? m : 10;
     if (q < p1) { double a, b; ols_tail(S, 1, ne, dm, a, b); return a * q + b; }
     if (q > pm) { double a, b; ols_tail(S, m - ne + 1, ne, dm, a, b); return a * q + b; }
-    if (q == pm || m == 1) return (double)S[m - 1];
+    if (q == pm || m == 1) return S(m - 1);
     int j = (int)floor(q * dm + 0.4);
     j = j < 1 ? 1 : (j > m - 1 ? m - 1 : j);
     while (j > 1 && pp_of(j, dm) > q) --j;
     while (j < m - 1 && pp_of(j + 1, dm) <= q) ++j;
     const double xj = pp_of(j, dm);
-    if (q == xj) return (double)S[j - 1];
-    const double yj = (double)S[j - 1], yj1 = (double)S[j];
+    if (q == xj) return S(j - 1);
+    const double yj = S(j - 1), yj1 = S(j);
     const double slope = (yj1 - yj) / (pp_of(j + 1, dm) - xj);
     return slope * (q - xj) + yj;
+}
+
+template <typename T>
+__device__ double inverse_cdf(int r, int n, int m, const T* __restrict__ S, double dn, double dm) {
+    auto acc = [&](int i) -> double { return (double)S[i]; };
+    return inverse_cdf_acc(r, n, m, acc, dn, dm);
 }
 
 // (x_j, shift_j) of member j of the group: shift = centred 9-sample mean of the climate-trend
@@ -324,6 +331,12 @@ static int launch_predict(const PredictParams& p, cudaStream_t st) {
     SDB_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+// fast tile kernels (qm_tile.cuh), float32 only, instantiated in qm_np256.cu / qm_np1024.cu
+int qm_fit_tile_np256(const FitParams& f, cudaStream_t st);
+int qm_fit_tile_np1024(const FitParams& f, cudaStream_t st);
+int qm_predict_tile_np256(int kind, const PredictParams& p, cudaStream_t st);
+int qm_predict_tile_np1024(int kind, const PredictParams& p, cudaStream_t st);
 
 // per-size entry points, defined in qm_np<N>.cu
 #define SDB_DECLARE_SIZE(NP)                                                             \

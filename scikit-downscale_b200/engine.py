@@ -37,10 +37,13 @@ def _stream() -> int:
 def _check_2d(t: torch.Tensor, name: str) -> int:
     if not t.is_cuda:
         raise RuntimeError(f'{name} must be a CUDA tensor (skdownscale_b200 has no CPU path)')
-    if t.dim() != 2 or t.stride(1) != 1:
+    if t.dim() != 2 or (t.stride(1) != 1 and t.shape[1] != 1):
         raise ValueError(f'{name} must be [time, cell] with the cell axis contiguous, got shape '
                          f'{tuple(t.shape)} strides {t.stride()}')
-    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    ld = t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+    if ld < t.shape[1]:
+        raise ValueError(f'{name}: rows overlap (shape {tuple(t.shape)}, strides {t.stride()})')
+    return ld
 
 
 def as_device(a, device, dtype=None) -> torch.Tensor:

@@ -37,7 +37,7 @@ def analog(T: int, Tq: int, C: int, p: int = 3, seed: int = 2, dtype=np.float32)
     """X_train [T,p,C], y_train [T,C], X_pred [Tq,p,C] — N(0,1) predictors, linear target + noise."""
     rng = np.random.default_rng(seed)
     X = rng.standard_normal((T, p, C))
-    w = np.array([1.0, 0.5, -0.3, 0.2, -0.1][:p])[None, :, None]
+    w = np.array([1.0, 0.5, -0.3, 0.2, -0.1, 0.4, -0.25, 0.15][:p])[None, :, None]
     y = (X * w).sum(axis=1) + 0.3 * rng.standard_normal((T, C))
     Xq = rng.standard_normal((Tq, p, C))
     return X.astype(dtype), y.astype(dtype), Xq.astype(dtype)

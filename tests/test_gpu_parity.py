@@ -38,6 +38,21 @@ def eng():
     return engine
 
 
+class force_generic:
+    """Run the generic (any dtype / any length) kernels instead of the float32 tile kernels."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        from skdownscale_b200 import _lib
+        self.old = _lib.load().sdb_set_debug_flags(1 if self.on else 0)
+
+    def __exit__(self, *a):
+        from skdownscale_b200 import _lib
+        _lib.load().sdb_set_debug_flags(self.old)
+
+
 def assert_close(got, ref, scale=1.0, rtol=RTOL):
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
@@ -102,8 +117,8 @@ def test_qm_group_too_long(dev):
 
 
 def test_qm_sorted_multiset_property(dev):
-    """n == m, tie-free: the mapped series of every cell is a permutation of the fitted one,
-    arranged in the rank order of the input (size-independent property, larger shape)."""
+    """n == m: the mapped value of every element is the fitted order statistic at its tie-max rank
+    (size-independent property, larger shape; exact equality, computed independently with torch)."""
     T, C = 10950, 512
     gen = torch.Generator(device=dev).manual_seed(0)
     y = torch.randn((T, C), device=dev, generator=gen)
@@ -111,8 +126,15 @@ def test_qm_sorted_multiset_property(dev):
     m = pm().QuantileMapper()
     m.fit_batched(y)
     out = m.transform_batched(x)
-    torch.testing.assert_close(torch.sort(out, dim=0).values, torch.sort(y, dim=0).values, rtol=0, atol=0)
-    torch.testing.assert_close(torch.argsort(out, dim=0), torch.argsort(x, dim=0), rtol=0, atol=0)
+    torch.testing.assert_close(out, _expected_rank_map(x, y), rtol=0, atol=0)
+
+
+def _expected_rank_map(x, y):
+    """sorted(y)[rank(x) - 1] per column, rank = number of elements <= x (ties take the highest)."""
+    ys = torch.sort(y, dim=0).values
+    xs = torch.sort(x, dim=0).values
+    r = torch.searchsorted(xs.T.contiguous(), x.T.contiguous(), right=True).T
+    return torch.gather(ys, 0, r - 1)
 
 
 # ------------------------------------------------------------------ BCSD
@@ -181,9 +203,16 @@ def test_bcsd_errors(dev):
         pm().BcsdTemperature().fit(pd.DataFrame(np.zeros((10, 1)), index=idx[:10]), pd.DataFrame(np.zeros((10, 1)), index=idx[5:15]))
 
 
+@pytest.mark.parametrize('generic', [False, True])
 @pytest.mark.parametrize('anoms', [True, False])
-def test_bcsd_temperature_vs_oracle_ranks(dev, anoms):
-    """30-year daily series, ragged cell count, NaN cells; ranks bit-exact, values 1e-5."""
+def test_bcsd_temperature_vs_oracle_ranks(dev, anoms, generic):
+    """30-year daily series, ragged cell count, NaN cells; ranks bit-exact, values 1e-5.
+    Both kernel families (float32 tile kernels / generic kernels) must give the same answer."""
+    with force_generic(generic):
+        _bcsd_temperature_vs_oracle_ranks(dev, anoms)
+
+
+def _bcsd_temperature_vs_oracle_ranks(dev, anoms):
     T, C = 10950, 37
     idx = synth.daily_index(T)
     Xtr, ytr, Xp = synth.temperature(T, C, seed=3)
@@ -210,7 +239,61 @@ def test_bcsd_temperature_vs_oracle_ranks(dev, anoms):
         assert yc[gi, 0] == oracle.bcsd._group_mean_like_pandas(ytr[rows, 0])
 
 
-def test_bcsd_precipitation_vs_oracle(dev):
+@pytest.mark.parametrize('case', ['outlier', 'clusters', 'constant', 'two_values'])
+@pytest.mark.parametrize('model', ['T', 'P'])
+def test_tile_kernel_bucket_fixups(dev, case, model):
+    """Inputs built to defeat the 22-bit key quantisation of the tile kernels: a huge outlier
+    squeezing every other value into one bucket (→ exact 64-bit fallback sort), clusters of
+    near-duplicates one float32 ulp apart (→ local exact fix-up), constant series and
+    two-valued series (→ exact-tie runs).  Ranks must still be bit-exact."""
+    T, C = 2922, 9
+    idx = synth.daily_index(T)
+    rng = np.random.default_rng(77)
+    Xtr, ytr, Xp = synth.temperature(T, C, seed=21)
+    if case == 'outlier':
+        Xp[::365, :] = 3.0e30
+        Xp[100::400, 1] = -2.5e29
+    elif case == 'clusters':
+        base = np.float32(12.5)
+        for c in range(C):
+            k = rng.integers(0, 40, T)
+            Xp[:, c] = np.nextafter(base, np.float32(100), dtype=np.float32) if False else base
+            for _ in range(3):      # spread over ~40 adjacent float32 values
+                pass
+            Xp[:, c] = (base.view(np.int32) + k.astype(np.int32)).view(np.float32)
+        Xp[5::7, 0] += 3.0
+    elif case == 'constant':
+        Xp[:] = np.float32(7.25)
+    elif case == 'two_values':
+        Xp[:] = np.where(rng.random((T, C)) < 0.6, np.float32(0.0), np.float32(1e-7))
+    groups = oracle.groups_from_keys(oracle.month_keys(idx))
+    if model == 'T':
+        m = pm().BcsdTemperature(return_anoms=False)
+    else:
+        m = pm().BcsdPrecipitation(return_anoms=False)
+    m.fit_batched(eng().as_device(Xtr, dev), eng().as_device(ytr, dev), idx)
+    out, rank = m.predict_batched(eng().as_device(Xp, dev), idx, want_rank=True)
+    out, rank = out.cpu().numpy(), rank.cpu().numpy()
+    for c in range(C):
+        if model == 'T':
+            st = oracle.bcsd_temperature_fit(Xtr[:, c], ytr[:, c], groups)
+            with np.errstate(all='ignore'):
+                o, r = oracle.bcsd_temperature_predict(st, Xp[:, c], groups, groups, False, return_rank=True)
+        else:
+            st = oracle.bcsd_precipitation_fit(ytr[:, c], groups, False)
+            o, r = oracle.bcsd_precipitation_predict(st, Xp[:, c], groups, False, return_rank=True)
+        assert np.array_equal(rank[:, c], r), f'{case}/{model}: rank mismatch in cell {c}'
+        if case != 'outlier':
+            assert_close(out[:, c], o.astype(np.float32), scale=np.std(ytr[:, c]))
+
+
+@pytest.mark.parametrize('generic', [False, True])
+def test_bcsd_precipitation_vs_oracle(dev, generic):
+    with force_generic(generic):
+        _bcsd_precipitation_vs_oracle(dev)
+
+
+def _bcsd_precipitation_vs_oracle(dev):
     T, C = 3653, 16
     idx = synth.daily_index(T)
     Xtr, ytr, Xp = synth.precipitation(T, C, seed=9)
@@ -253,8 +336,9 @@ def test_bcsd_custom_grouper_and_strided_views(dev):
 
 
 def test_bcsd_abs_multiset_property(dev):
-    """return_anoms=False, same index: (out - shift) of every month group is a permutation of the
-    fitted y of that group — checked via sums on a larger block (size-independent)."""
+    """pure per-month quantile mapping (BcsdPrecipitation, return_anoms=False) of X onto y's
+    distribution: every element equals the fitted order statistic of its month at its tie-max
+    rank — exact equality on a larger block, expectation computed independently with torch."""
     T, C = 10950, 1024
     idx = synth.daily_index(T)
     gen = torch.Generator(device=dev).manual_seed(1)
@@ -267,7 +351,7 @@ def test_bcsd_abs_multiset_property(dev):
     month = torch.as_tensor(np.asarray(idx.month), device=dev)
     for mo in (1, 2, 7, 12):
         sel = month == mo
-        torch.testing.assert_close(torch.sort(out[sel], dim=0).values, torch.sort(ytr[sel], dim=0).values, rtol=0, atol=0)
+        torch.testing.assert_close(out[sel], _expected_rank_map(Xtr[sel], ytr[sel]), rtol=0, atol=0)
 
 
 # ------------------------------------------------------------------ GARD
