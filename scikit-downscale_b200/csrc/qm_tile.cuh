@@ -34,7 +34,7 @@ __device__ __forceinline__ int skew(int j) { return j + (j >> 5); }
 template <int E>
 constexpr size_t fit_tile_smem() { return (size_t)TILE_CT * TileGeom<E>::NPS * 4; }
 template <int E>
-constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * (2 * TileGeom<E>::NPS * 4 + TileGeom<E>::NP * 2); }
+constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 3 * TileGeom<E>::NPS * 4; }
 
 // cooperative, coalesced load of one group's rows for the CTA's 8 cells into tile[cell][skew(j)]
 template <int E>
@@ -99,42 +99,51 @@ qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
 }
 
 // ---------------------------------------------------------------- predict helpers
-// window sum / count of the centred 9-sample window of member j (members outside [0, n) absent)
-__device__ __forceinline__ double window_key(const float* myX, int n, int j, double xc, double& shift) {
+// sum / cnt for the window counts 5..9, correctly rounded: q0 = sum*rc, one FMA residual
+// correction (Markstein).  cnt == 9 everywhere except the first / last four members of a group.
+__device__ __forceinline__ double div_count(double sum, int cnt) {
+    if (cnt == 9) {
+        const double rc = 1.0 / 9.0;
+        const double q0 = sum * rc;
+        const double r = fma(-q0, 9.0, sum);
+        return fma(r, rc, q0);
+    }
+    return sum / (double)cnt;
+}
+
+// window bounds of member j inside a group of n
+__device__ __forceinline__ int win_count(int j, int n) {
+    const int lo = j - 4 < 0 ? 0 : j - 4, hi = j + 4 > n - 1 ? n - 1 : j + 4;
+    return hi - lo + 1;
+}
+
+// exact rank key of member j as the reference computes it: x - (rolling mean - xc) in float64
+__device__ __forceinline__ double window_key(const float* myX, int n, int j, double xc) {
     double acc = 0.0;
     const int lo = j - 4 < 0 ? 0 : j - 4, hi = j + 4 > n - 1 ? n - 1 : j + 4;
     for (int jj = lo; jj <= hi; ++jj) acc += (double)myX[skew(jj)];
-    shift = acc / (double)(hi - lo + 1) - xc;
-    return (double)myX[skew(j)] - shift;
+    return (double)myX[skew(j)] - (div_count(acc, hi - lo + 1) - xc);
+}
+template <bool SHIFT>
+__device__ __forceinline__ double exact_key(const float* myX, int n, int j, double xc) {
+    if (SHIFT) return window_key(myX, n, j, xc);
+    return (double)(myX[skew(j)] + 0.0f);
 }
 
-// Visit the E members owned by this lane: f(e, x, shift) with shift = rolling mean - xc in float64.
-// The window sum slides (add the entering value, subtract the leaving one): exact for float32
-// data of ordinary dynamic range, like pandas' own online add/remove kernel.
-template <int E, bool EXACT, class F>
-__device__ __forceinline__ void visit_shift(const float* myX, int n, int j0, double xc, F&& f) {
-    float xh[E + 9];                                   // members j0-4 .. j0+E+4
-#pragma unroll
-    for (int i = 0; i < E + 9; ++i) {
-        const int jj = j0 - 4 + i;
-        xh[i] = (jj >= 0 && jj < n) ? myX[skew(jj)] : 0.0f;
-    }
+// Sliding 9-sample window over the members [j0, j0+cnt) owned by one lane, values read from the
+// shared-memory row: f(j, x_j, window_sum_j).  The sum slides (add the entering member, subtract
+// the leaving one) — exact for float32 data of ordinary dynamic range, like pandas' own online
+// add/remove kernel (pandas/_libs/window/aggregations.pyx roll_mean).
+template <class F>
+__device__ __forceinline__ void slide_window(const float* myX, int n, int j0, int j1, F&& f) {
+    if (j0 >= j1) return;
     double sum = 0.0;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) sum += (double)xh[i];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int j = j0 + e;
-        if (j < n) {
-            const int lo = j - 4 < 0 ? 0 : j - 4, hi = j + 4 > n - 1 ? n - 1 : j + 4;
-            const int cnt = hi - lo + 1;
-            double roll;
-            if (EXACT) roll = sum / (double)cnt;
-            else       roll = sum * (1.0 / 9.0) * (9.0 / (double)cnt);      // bounds only
-            f(e, (double)xh[e + 4], roll - xc);
-        }
-        sum += (double)xh[e + 9];
-        sum -= (double)xh[e];
+    for (int jj = (j0 - 4 < 0 ? 0 : j0 - 4); jj <= (j0 + 4 > n - 1 ? n - 1 : j0 + 4); ++jj) sum += (double)myX[skew(jj)];
+#pragma unroll 2
+    for (int j = j0; j < j1; ++j) {
+        f(j, myX[skew(j)], sum);
+        if (j + 5 < n) sum += (double)myX[skew(j + 5)];
+        if (j - 4 >= 0) sum -= (double)myX[skew(j - 4)];
     }
 }
 
@@ -149,10 +158,12 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// run ends (1-based count) of equal-bucket runs over the first n sorted positions, blocked layout
+// run [start, end) of equal-bucket sorted positions around every position, packed
+// start | end << 10 (blocked layout, first n positions real).  O(1) per position: boundary
+// bitmaps per lane + one ballot each way.
 template <int E, int LOG>
 __device__ __forceinline__ void bucket_run_bounds(const K32 (&v)[E], int lane, int n, uint32_t nxt_first,
-                                                  uint32_t prv_last, int (&run_end)[E], int (&run_start)[E]) {
+                                                  uint32_t prv_last, uint32_t (&packed)[E]) {
     uint32_t bm_last = 0, bm_first = 0;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
@@ -165,15 +176,12 @@ __device__ __forceinline__ void bucket_run_bounds(const K32 (&v)[E], int lane, i
         bm_last |= last ? (1u << e) : 0u;
         bm_first |= first ? (1u << e) : 0u;
     }
-    if (E < 32) { bm_last &= (1u << E) - 1u; bm_first &= (1u << E) - 1u; }
     const int base = lane * E;
-    // ends: nearest "last" at or after p
-    const int minb = base + __ffs(bm_last);
+    const int minb = base + __ffs(bm_last);                          // nearest run end at/after the lane start
     const uint32_t has_l = __ballot_sync(0xffffffffu, bm_last != 0);
     const uint32_t higher = (lane == 31) ? 0u : (has_l & ~((2u << lane) - 1u));
     const int carry_e = __shfl_sync(0xffffffffu, minb, higher ? (__ffs(higher) - 1) : lane);
-    // starts: nearest "first" at or before p
-    const int maxf = base + (31 - __clz(bm_first | 0u));           // valid when bm_first != 0
+    const int maxf = base + (31 - __clz(bm_first | 1u));             // nearest run start at/before the lane end
     const uint32_t has_f = __ballot_sync(0xffffffffu, bm_first != 0);
     const uint32_t lower = has_f & ((1u << lane) - 1u);
     const int carry_s = __shfl_sync(0xffffffffu, maxf, lower ? (31 - __clz(lower)) : lane);
@@ -181,14 +189,114 @@ __device__ __forceinline__ void bucket_run_bounds(const K32 (&v)[E], int lane, i
 #pragma unroll
     for (int e = E - 1; e >= 0; --e) {
         if ((bm_last >> e) & 1u) cur = base + e + 1;
-        run_end[e] = cur;
+        packed[e] = (uint32_t)cur << 10;
     }
     cur = carry_s;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         if ((bm_first >> e) & 1u) cur = base + e;
-        run_start[e] = cur;
+        packed[e] |= (uint32_t)cur;
     }
+}
+
+// Out-of-line exact ranking of one (cell, group): 64-bit key + position sort (the generic
+// algorithm) for the rare group whose keys defeat the bucket quantisation (a long bucket holding
+// distinct keys).  Writes the 1-based tie-max rank of member j to R[skew(j)].
+template <int E, bool SHIFT>
+__device__ __noinline__ void rank_exact64(const float* myX, int n, double xc, int lane, uint32_t* R) {
+    K64I u[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int j = lane * E + e;
+        u[e] = (j < n) ? make_rank_item64(exact_key<SHIFT>(myX, n, j, xc), (uint32_t)j) : sentinel_item<K64I>((uint32_t)j);
+    }
+    sort_blocked<K64I, E, 32>(u, lane, nullptr);
+    int r2[E];
+    tie_max_ranks<K64I, E, 32>(u, lane, r2, nullptr);
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+        if (u[e].i < (uint32_t)n) R[skew((int)u[e].i)] = (uint32_t)r2[e];
+}
+
+// Exact ranks when some bucket holds several members.  sw[] holds the sorted packed words
+// (bucket << LOG | member), R[] receives start | end << 10 | B << 21 per sorted position and,
+// at the end, the rank of member j at R[skew(j)].  Runtime loops over shared memory only.
+template <int E, int LOG, bool SHIFT>
+__device__ __noinline__ bool rank_with_ties(const float* myX, uint32_t* sw, uint32_t* R, int n, double xc, int lane) {
+    constexpr uint32_t IDX = (1u << LOG) - 1u;
+    const int p0 = lane * E, p1 = (p0 + E < n) ? p0 + E : n;
+    // bad pair (pos, pos+1): same bucket, different exact keys
+    uint32_t bm_bad = 0;
+    for (int pos = p0; pos < p1; ++pos) {
+        const uint32_t pk = R[skew(pos)];
+        const int en = (int)((pk >> 10) & 0x7ffu);
+        if (pos + 1 < en) {
+            const double a = exact_key<SHIFT>(myX, n, (int)(sw[skew(pos)] & IDX), xc);
+            const double b = exact_key<SHIFT>(myX, n, (int)(sw[skew(pos + 1)] & IDX), xc);
+            if (a != b) bm_bad |= 1u << (pos - p0);
+        }
+    }
+    if (!__any_sync(0xffffffffu, bm_bad != 0)) {
+        // multi-member buckets hold exact ties only: every member takes the end of its run
+        __syncwarp();
+        uint32_t rk[1];
+        (void)rk;
+        // ranks are scattered by member position; the run table is still needed by other lanes
+        // only through R[pos] of THEIR positions, so stage through sw (idx | rank << LOG)
+        for (int pos = p0; pos < p1; ++pos) {
+            const uint32_t en = (R[skew(pos)] >> 10) & 0x7ffu;
+            sw[skew(pos)] = (sw[skew(pos)] & IDX) | (en << LOG);
+        }
+        __syncwarp();
+        for (int pos = p0; pos < p1; ++pos) {
+            const uint32_t t = sw[skew(pos)];
+            R[skew((int)(t & IDX))] = t >> LOG;
+        }
+        return true;
+    }
+    // exclusive prefix count of bad pairs over sorted positions → B, packed into R[pos] bits 21..31
+    const int mine = __popc(bm_bad);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int before = incl - mine;
+    for (int pos = p0; pos < p1; ++pos) {
+        const uint32_t B = (uint32_t)(before + __popc(bm_bad & ((1u << (pos - p0)) - 1u)));
+        R[skew(pos)] |= B << 21;
+    }
+    __syncwarp();
+    bool need_fallback = false;
+    for (int pos = p0; pos < p1; ++pos) {
+        const uint32_t pk = R[skew(pos)];
+        const int s = (int)(pk & 0x3ffu), en = (int)((pk >> 10) & 0x7ffu);
+        const int L = en - s;
+        int r;
+        if (L == 1) r = pos + 1;
+        else {
+            const int nbad = (int)(R[skew(en - 1)] >> 21) - (int)(R[skew(s)] >> 21);
+            if (nbad == 0) r = en;
+            else if (L > TILE_LMAX) { need_fallback = true; r = en; }
+            else {
+                const double kp = exact_key<SHIFT>(myX, n, (int)(sw[skew(pos)] & IDX), xc);
+                int cnt = 0;
+                for (int q2 = s; q2 < en; ++q2)
+                    cnt += exact_key<SHIFT>(myX, n, (int)(sw[skew(q2)] & IDX), xc) <= kp ? 1 : 0;
+                r = s + cnt;
+            }
+        }
+        // members keep their identity in the low bits, so other lanes may still read sw[pos] & IDX
+        sw[skew(pos)] = (sw[skew(pos)] & IDX) | ((uint32_t)r << LOG);
+    }
+    __syncwarp();
+    if (__any_sync(0xffffffffu, need_fallback)) return false;
+    for (int pos = p0; pos < p1; ++pos) {
+        const uint32_t t = sw[skew(pos)];
+        R[skew((int)(t & IDX))] = t >> LOG;
+    }
+    return true;
 }
 
 // ---------------------------------------------------------------- predict
@@ -196,19 +304,19 @@ template <int E, bool SHIFT>
 __global__ void __launch_bounds__(TILE_THREADS, 2)
 qm_predict_tile_kernel(const PredictParams p) {
     using G = TileGeom<E>;
-    constexpr int NP = G::NP, NPS = G::NPS, LOG = G::LOG;
+    constexpr int NPS = G::NPS, LOG = G::LOG;
     constexpr uint32_t QMAX = G::QMAX;
+    constexpr uint32_t IDX = (1u << LOG) - 1u;
     extern __shared__ uint32_t smem_u[];
-    float* tileX = reinterpret_cast<float*>(smem_u);
-    float* tileS = tileX + TILE_CT * NPS;
-    uint16_t* rank_all = reinterpret_cast<uint16_t*>(tileS + TILE_CT * NPS);
+    float* tileX = reinterpret_cast<float*>(smem_u);                  // inputs of the group, later unused
+    float* tileS = tileX + TILE_CT * NPS;                             // sorted words → fitted values → outputs
+    uint32_t* tileR = reinterpret_cast<uint32_t*>(tileS + TILE_CT * NPS);   // run table → ranks → mapped values
 
     const int g = blockIdx.y;
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
     const int n = p.len[g];
     const int32_t* rg = p.rows + (int64_t)g * p.max_len;
-    const float* X = (const float*)p.X;
-    load_tile<E>(tileX, X, p.ld, p.C, c0, rg, n, p.valid);
+    load_tile<E>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -216,13 +324,14 @@ qm_predict_tile_kernel(const PredictParams p) {
     float* myX = tileX + warp * NPS;
     float* myS = tileS + warp * NPS;
     uint32_t* sw = reinterpret_cast<uint32_t*>(myS);
-    uint16_t* myR = rank_all + warp * NP;
+    uint32_t* R = tileR + warp * NPS;
     const int j0 = lane * E;
+    const int j1 = (j0 + E < n) ? j0 + E : n;
     const bool in_range = c < p.C;
     const bool active = in_range && (!p.valid || p.valid[c]);
 
     if (in_range && !active) {
-        for (int j = lane; j < n; j += 32) myX[skew(j)] = NAN;
+        for (int j = lane; j < n; j += 32) myS[skew(j)] = NAN;
     } else if (active) {
         const int sg = p.state_gid[g];
         const int m = p.fit_len[sg];
@@ -231,153 +340,79 @@ qm_predict_tile_kernel(const PredictParams p) {
         if (SHIFT) xc = (double)((const float*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
         if (p.mode != SDB_MODE_QM && p.return_anoms) yc = (double)((const float*)p.y_climo)[(int64_t)sg * p.ld_climo + c];
 
-        // ---- 1. monotone quantisation of the rank keys, packed with the member position
-        K32 v[E];
-        {
-            float lo32 = INFINITY, hi32 = -INFINITY;
-            bool bad = false;
-            if (SHIFT) {
-                visit_shift<E, false>(myX, n, j0, xc, [&](int, double x, double s) {
-                    const double k = x - s;
-                    lo32 = fminf(lo32, __double2float_rd(k));
-                    hi32 = fmaxf(hi32, __double2float_ru(k));
-                    bad |= !isfinite(x);
-                });
-            } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    if (j0 + e < n) {
-                        const float x = myX[skew(j0 + e)];
-                        lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x);
-                        bad |= !isfinite(x);
-                    }
-                }
+        // ---- 1. bounds of the rank keys, then monotone quantisation packed with the member position
+        float lo32 = INFINITY, hi32 = -INFINITY;
+        bool bad = false;
+        if (SHIFT) {
+            slide_window(myX, n, j0, j1, [&](int j, float x, double sum) {
+                const double k = (double)x - (sum * (1.0 / (double)win_count(j, n)) - xc);   // approximate: bounds only
+                lo32 = fminf(lo32, __double2float_rd(k));
+                hi32 = fmaxf(hi32, __double2float_ru(k));
+                bad |= !isfinite(x);
+            });
+        } else {
+            for (int j = j0; j < j1; ++j) {
+                const float x = myX[skew(j)];
+                lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x);
+                bad |= !isfinite(x);
             }
-            if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
-            lo32 = warp_min(lo32); hi32 = warp_max(hi32);
-            if (SHIFT) {
-                // the bounds came from an approximate rolling mean: widen them by a few float32 ulps
-                const double lo = (double)lo32 - fabs((double)lo32) * 1e-6 - 1e-30;
-                const double hi = (double)hi32 + fabs((double)hi32) * 1e-6 + 1e-30;
-                const double scale = (hi > lo && isfinite(hi - lo)) ? (double)(QMAX - 1) / (hi - lo) : 0.0;
-                visit_shift<E, true>(myX, n, j0, xc, [&](int e, double x, double s) {
-                    const double t = ((x - s) - lo) * scale;
-                    uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;      // also maps NaN to 0
-                    q = q > QMAX - 1 ? QMAX - 1 : q;
-                    v[e].k = (q << LOG) | (uint32_t)(j0 + e);
-                });
-            } else {
-                const float range = hi32 - lo32;
-                const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    if (j0 + e < n) {
-                        const float t = (myX[skew(j0 + e)] - lo32) * scale;
-                        uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
-                        q = q > QMAX - 1 ? QMAX - 1 : q;
-                        v[e].k = (q << LOG) | (uint32_t)(j0 + e);
-                    }
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < E; ++e)
-                if (j0 + e >= n) v[e].k = 0xffffffffu;
         }
+        if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
+        lo32 = warp_min(lo32); hi32 = warp_max(hi32);
+        if (SHIFT) {
+            // bounds came from an approximate mean: widen by a few float32 ulps
+            const double lo = (double)lo32 - fabs((double)lo32) * 1e-6 - 1e-30;
+            const double hi = (double)hi32 + fabs((double)hi32) * 1e-6 + 1e-30;
+            const double scale = (hi > lo && isfinite(hi - lo)) ? (double)(QMAX - 1) / (hi - lo) : 0.0;
+            slide_window(myX, n, j0, j1, [&](int j, float x, double sum) {
+                const double key = (double)x - (div_count(sum, win_count(j, n)) - xc);
+                const double t = (key - lo) * scale;
+                uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;          // also maps NaN to 0
+                q = q > QMAX - 1 ? QMAX - 1 : q;
+                sw[skew(j)] = (q << LOG) | (uint32_t)j;
+            });
+        } else {
+            const float range = hi32 - lo32;
+            const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
+            for (int j = j0; j < j1; ++j) {
+                const float t = (myX[skew(j)] - lo32) * scale;
+                uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
+                q = q > QMAX - 1 ? QMAX - 1 : q;
+                sw[skew(j)] = (q << LOG) | (uint32_t)j;
+            }
+        }
+        K32 v[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) v[e].k = (j0 + e < n) ? sw[skew(j0 + e)] : 0xffffffffu;
 
-        // ---- 2. sort, then 1-based tie-max ranks
+        // ---- 2. one 32-bit keys-only sort, then 1-based tie-max ranks → R[member]
         sort_blocked<K32, E, 32>(v, lane, nullptr);
         const uint32_t nxt_first = __shfl_down_sync(0xffffffffu, v[0].k, 1);
-        const uint32_t prv_last = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
         bool any_eq = false;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            const int pos = j0 + e;
             const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-            any_eq |= (pos + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG));
+            any_eq |= (j0 + e + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG));
         }
-        constexpr uint32_t IDX = (uint32_t)NP - 1u;
         if (!__any_sync(0xffffffffu, any_eq)) {
-            // every bucket holds one member: sorted position = rank - 1
+            // every bucket holds one member: rank = sorted position + 1
 #pragma unroll
             for (int e = 0; e < E; ++e)
-                if (j0 + e < n) myR[v[e].k & IDX] = (uint16_t)(j0 + e + 1);
+                if (j0 + e < n) R[skew((int)(v[e].k & IDX))] = (uint32_t)(j0 + e + 1);
         } else {
-            // exact key of member j (what the reference compares): the value itself, or x - shift in float64
-            auto exact_key = [&](int j) -> double {
-                if (SHIFT) { double s; return window_key(myX, n, j, xc, s); }
-                return (double)(myX[skew(j)] + 0.0f);
-            };
-            int run_end[E], run_start[E];
-            bucket_run_bounds<E, LOG>(v, lane, n, nxt_first, prv_last, run_end, run_start);
-            // bad pair = neighbours in one bucket whose exact keys differ
-            uint32_t bm_bad = 0;
+            const uint32_t prv_last = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
+            uint32_t packed[E];
+            bucket_run_bounds<E, LOG>(v, lane, n, nxt_first, prv_last, packed);
+            __syncwarp();
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int pos = j0 + e;
-                const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-                if ((pos + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG))) {
-                    if (exact_key((int)(v[e].k & IDX)) != exact_key((int)(kn & IDX))) bm_bad |= 1u << e;
-                }
+                sw[skew(j0 + e)] = v[e].k;
+                R[skew(j0 + e)] = packed[e];
             }
-            if (!__any_sync(0xffffffffu, bm_bad != 0)) {
-                // buckets with several members hold exact ties only: everyone takes the run end
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                    if (j0 + e < n) myR[v[e].k & IDX] = (uint16_t)run_end[e];
-            } else {
-                // exclusive prefix count of bad pairs over sorted positions → B[pos] (stored in myR for now)
-                const int mine = __popc(bm_bad);
-                int incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                int run = incl - mine;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    sw[skew(j0 + e)] = v[e].k;
-                    myR[j0 + e] = (uint16_t)run;
-                    run += (bm_bad >> e) & 1u;
-                }
+            __syncwarp();
+            if (!rank_with_ties<E, LOG, SHIFT>(myX, sw, R, n, xc, lane)) {
                 __syncwarp();
-                int r[E];
-                bool need_fallback = false;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {      // unrolled: v / run bounds must stay in registers
-                    const int pos = j0 + e;
-                    if (pos >= n) { r[e] = 0; continue; }
-                    const int s = run_start[e], en = run_end[e];
-                    const int L = en - s;
-                    if (L == 1) { r[e] = pos + 1; continue; }
-                    const int nbad = (int)myR[en - 1] - (int)myR[s];
-                    if (nbad == 0) { r[e] = en; continue; }
-                    if (L > TILE_LMAX) { need_fallback = true; r[e] = en; continue; }
-                    const double kp = exact_key((int)(v[e].k & IDX));
-                    int cnt = 0;
-                    for (int q2 = s; q2 < en; ++q2) cnt += exact_key((int)(sw[skew(q2)] & IDX)) <= kp ? 1 : 0;
-                    r[e] = s + cnt;
-                }
-                __syncwarp();
-                if (!__any_sync(0xffffffffu, need_fallback)) {
-#pragma unroll
-                    for (int e = 0; e < E; ++e)
-                        if (j0 + e < n) myR[v[e].k & IDX] = (uint16_t)r[e];
-                } else {
-                    // a long bucket with distinct keys (e.g. an outlier squeezing the rest): exact 64-bit sort
-                    K64I u[E];
-#pragma unroll
-                    for (int e = 0; e < E; ++e) {
-                        const int j = j0 + e;
-                        u[e] = (j < n) ? make_rank_item64(exact_key(j), (uint32_t)j) : sentinel_item<K64I>((uint32_t)j);
-                    }
-                    sort_blocked<K64I, E, 32>(u, lane, nullptr);
-                    int r2[E];
-                    tie_max_ranks<K64I, E, 32>(u, lane, r2, nullptr);
-#pragma unroll
-                    for (int e = 0; e < E; ++e)
-                        if (u[e].i < (uint32_t)n) myR[u[e].i] = (uint16_t)r2[e];
-                }
+                rank_exact64<E, SHIFT>(myX, n, xc, lane, R);
             }
         }
         __syncwarp();
@@ -386,46 +421,43 @@ qm_predict_tile_kernel(const PredictParams p) {
         for (int j = lane; j < m; j += 32) myS[skew(j)] = S[j];
         __syncwarp();
 
-        // ---- 4. rank → quantile → inverse CDF → output, in member order
-        const double dn = pp_denominator(n), dm = pp_denominator(m);
-        auto Sat = [&](int i) -> double { return (double)myS[skew(i)]; };
-        float o[E];
-        auto finish = [&](int e, double shift) {
-            const int j = j0 + e;
-            const int rk = (int)myR[j];
-            const double val = inverse_cdf_acc(rk, n, m, Sat, dn, dm);
-            double res;
-            if (SHIFT) {
-                res = shift + val;                               // bcsd.py:263
-                if (p.return_anoms) res = res - yc;              // bcsd.py:267
-            } else if (p.mode == SDB_MODE_BCSD_P) {
-                res = p.return_anoms ? val / yc : val;           // bcsd.py:170-185
-            } else {
-                res = val;
+        // ---- 4. rank → quantile → inverse CDF, value parked (float32) in place of the rank
+        {
+            const double dn = pp_denominator(n), dm = pp_denominator(m);
+            auto Sat = [&](int i) -> double { return (double)myS[skew(i)]; };
+#pragma unroll 2
+            for (int j = j0; j < j1; ++j) {
+                const int rk = (int)R[skew(j)];
+                if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
+                R[skew(j)] = __float_as_uint((float)inverse_cdf_acc(rk, n, m, Sat, dn, dm));
             }
-            o[e] = (float)res;
-            if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
-        };
-        if (SHIFT) {
-            visit_shift<E, true>(myX, n, j0, xc, [&](int e, double, double s) { finish(e, s); });
-        } else {
-#pragma unroll
-            for (int e = 0; e < E; ++e)
-                if (j0 + e < n) finish(e, 0.0);
         }
         __syncwarp();
-#pragma unroll
-        for (int e = 0; e < E; ++e)
-            if (j0 + e < n) myX[skew(j0 + e)] = o[e];
+
+        // ---- 5. output in member order (the fitted values are no longer needed: reuse their row)
+        if (SHIFT) {
+            slide_window(myX, n, j0, j1, [&](int j, float, double sum) {
+                const double shift = div_count(sum, win_count(j, n)) - xc;
+                double res = shift + (double)__uint_as_float(R[skew(j)]);     // bcsd.py:263
+                if (p.return_anoms) res = res - yc;                           // bcsd.py:267
+                myS[skew(j)] = (float)res;
+            });
+        } else {
+            for (int j = j0; j < j1; ++j) {
+                const double val = (double)__uint_as_float(R[skew(j)]);
+                const double res = (p.mode == SDB_MODE_BCSD_P && p.return_anoms) ? val / yc : val;   // bcsd.py:170-185
+                myS[skew(j)] = (float)res;
+            }
+        }
     }
     __syncthreads();
-    // ---- 5. coalesced store of the tile (rows of 8 cells)
+    // ---- 6. coalesced store of the tile (rows of 8 cells)
     {
         const int cc = threadIdx.x & (TILE_CT - 1);
         const int64_t cs = c0 + cc;
         if (cs < p.C) {
             float* outp = (float*)p.out + cs;
-            const float* srcp = tileX + cc * NPS;
+            const float* srcp = tileS + cc * NPS;
 #pragma unroll 4
             for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT)
                 __stcs(outp + (int64_t)rg[j] * p.ld_out, srcp[skew(j)]);
