@@ -308,9 +308,9 @@ qm_predict_tile_kernel(const PredictParams p) {
     constexpr uint32_t QMAX = G::QMAX;
     constexpr uint32_t IDX = (1u << LOG) - 1u;
     extern __shared__ uint32_t smem_u[];
-    float* tileX = reinterpret_cast<float*>(smem_u);                  // inputs of the group, later unused
-    float* tileS = tileX + TILE_CT * NPS;                             // sorted words → fitted values → outputs
-    uint32_t* tileR = reinterpret_cast<uint32_t*>(tileS + TILE_CT * NPS);   // run table → ranks → mapped values
+    float* tileX = reinterpret_cast<float*>(smem_u);                  // inputs of the group
+    float* tileS = tileX + TILE_CT * NPS;                             // (slow path) sorted words → fitted values
+    uint32_t* tileR = reinterpret_cast<uint32_t*>(tileS + TILE_CT * NPS);   // (run table →) ranks/values → outputs
 
     const int g = blockIdx.y;
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
@@ -331,7 +331,7 @@ qm_predict_tile_kernel(const PredictParams p) {
     const bool active = in_range && (!p.valid || p.valid[c]);
 
     if (in_range && !active) {
-        for (int j = lane; j < n; j += 32) myS[skew(j)] = NAN;
+        for (int j = lane; j < n; j += 32) R[skew(j)] = __float_as_uint(NAN);
     } else if (active) {
         const int sg = p.state_gid[g];
         const int m = p.fit_len[sg];
@@ -339,53 +339,83 @@ qm_predict_tile_kernel(const PredictParams p) {
         double xc = 0.0, yc = 0.0;
         if (SHIFT) xc = (double)((const float*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
         if (p.mode != SDB_MODE_QM && p.return_anoms) yc = (double)((const float*)p.y_climo)[(int64_t)sg * p.ld_climo + c];
+        const bool ratio = (p.mode == SDB_MODE_BCSD_P) && p.return_anoms;
 
-        // ---- 1. bounds of the rank keys, then monotone quantisation packed with the member position
+        // ---- 1. own members (+ 4 / 5 halo) to registers; key bounds from the plain value range
+        constexpr int HL = SHIFT ? 4 : 0, HR = SHIFT ? 5 : 0;
+        float xh[E + HL + HR];
+        {
+            const int rb = skew(j0);
+#pragma unroll
+            for (int i = 0; i < E + HL + HR; ++i) {
+                const int e = i - HL;                          // member offset inside / around the lane's block
+                const int jj = j0 + e;
+                // E == 32: the skew step only changes at the block edges → static offsets from the row base
+                const int addr = (E == 32) ? rb + e + (e < 0 ? -1 : (e >= 32 ? 1 : 0)) : skew(jj < 0 ? 0 : jj);
+                xh[i] = (jj >= 0 && jj < n) ? myX[addr] : 0.0f;
+            }
+        }
         float lo32 = INFINITY, hi32 = -INFINITY;
         bool bad = false;
-        if (SHIFT) {
-            slide_window(myX, n, j0, j1, [&](int j, float x, double sum) {
-                const double k = (double)x - (sum * (1.0 / (double)win_count(j, n)) - xc);   // approximate: bounds only
-                lo32 = fminf(lo32, __double2float_rd(k));
-                hi32 = fmaxf(hi32, __double2float_ru(k));
-                bad |= !isfinite(x);
-            });
-        } else {
-            for (int j = j0; j < j1; ++j) {
-                const float x = myX[skew(j)];
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (j0 + e < n) {
+                const float x = xh[e + HL];
                 lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x);
                 bad |= !isfinite(x);
             }
         }
         if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
         lo32 = warp_min(lo32); hi32 = warp_max(hi32);
+
+        // ---- 2. exact rank keys → monotone bucket number, packed with the member position.
+        // Bounds are a guess (value range + 1/8 margin, centred on the climatology for the shifted
+        // key); out-of-range keys clamp to the end buckets, which keeps the map monotone — the
+        // exact fix-up below sorts out whatever shares a bucket.
+        K32 v[E];
+        float sh[SHIFT ? E : 1];
         if (SHIFT) {
-            // bounds came from an approximate mean: widen by a few float32 ulps
-            const double lo = (double)lo32 - fabs((double)lo32) * 1e-6 - 1e-30;
-            const double hi = (double)hi32 + fabs((double)hi32) * 1e-6 + 1e-30;
+            const double range = (double)hi32 - (double)lo32;
+            const double lo = (double)lo32 - 0.125 * range, hi = (double)hi32 + 0.125 * range;
             const double scale = (hi > lo && isfinite(hi - lo)) ? (double)(QMAX - 1) / (hi - lo) : 0.0;
-            slide_window(myX, n, j0, j1, [&](int j, float x, double sum) {
-                const double key = (double)x - (div_count(sum, win_count(j, n)) - xc);
-                const double t = (key - lo) * scale;
-                uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;          // also maps NaN to 0
-                q = q > QMAX - 1 ? QMAX - 1 : q;
-                sw[skew(j)] = (q << LOG) | (uint32_t)j;
-            });
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sum += (double)xh[i];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int j = j0 + e;
+                if (j < n) {
+                    const double shift = div_count(sum, win_count(j, n)) - xc;
+                    const double t = (((double)xh[e + 4] - shift) - lo) * scale;
+                    uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
+                    q = q > QMAX - 1 ? QMAX - 1 : q;
+                    v[e].k = (q << LOG) | (uint32_t)j;
+                    sh[e] = (float)shift;
+                } else {
+                    v[e].k = 0xffffffffu;
+                    sh[e] = 0.0f;
+                }
+                sum += (double)xh[e + 9];
+                sum -= (double)xh[e];
+            }
         } else {
             const float range = hi32 - lo32;
             const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
-            for (int j = j0; j < j1; ++j) {
-                const float t = (myX[skew(j)] - lo32) * scale;
-                uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
-                q = q > QMAX - 1 ? QMAX - 1 : q;
-                sw[skew(j)] = (q << LOG) | (uint32_t)j;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int j = j0 + e;
+                if (j < n) {
+                    const float t = (xh[e] - lo32) * scale;
+                    uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
+                    q = q > QMAX - 1 ? QMAX - 1 : q;
+                    v[e].k = (q << LOG) | (uint32_t)j;
+                } else {
+                    v[e].k = 0xffffffffu;
+                }
             }
         }
-        K32 v[E];
-#pragma unroll
-        for (int e = 0; e < E; ++e) v[e].k = (j0 + e < n) ? sw[skew(j0 + e)] : 0xffffffffu;
 
-        // ---- 2. one 32-bit keys-only sort, then 1-based tie-max ranks → R[member]
+        // ---- 3. one 32-bit keys-only sort
         sort_blocked<K32, E, 32>(v, lane, nullptr);
         const uint32_t nxt_first = __shfl_down_sync(0xffffffffu, v[0].k, 1);
         bool any_eq = false;
@@ -394,16 +424,45 @@ qm_predict_tile_kernel(const PredictParams p) {
             const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
             any_eq |= (j0 + e + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG));
         }
+        const bool same = (n == m);
+        bool ranks_in_R = false;        // false: R[member] already holds the mapped value (float bits)
+        auto park = [&](float val) -> uint32_t { return __float_as_uint(ratio ? (float)((double)val / yc) : val); };
+
         if (!__any_sync(0xffffffffu, any_eq)) {
-            // every bucket holds one member: rank = sorted position + 1
+            if (same) {
+                // one member per bucket, same length: the member at sorted position pos takes the
+                // fitted order statistic S[pos] — read straight from the state record
+                const bool vec = ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+                if (vec && E % 4 == 0) {
 #pragma unroll
-            for (int e = 0; e < E; ++e)
-                if (j0 + e < n) R[skew((int)(v[e].k & IDX))] = (uint32_t)(j0 + e + 1);
+                    for (int e = 0; e < E; e += 4) {
+                        if (j0 + e + 3 < n) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(S + j0 + e);
+                            R[skew((int)(v[e].k & IDX))] = park(s4.x);
+                            R[skew((int)(v[e + 1].k & IDX))] = park(s4.y);
+                            R[skew((int)(v[e + 2].k & IDX))] = park(s4.z);
+                            R[skew((int)(v[e + 3].k & IDX))] = park(s4.w);
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < 4; ++d)
+                                if (j0 + e + d < n) R[skew((int)(v[e + d].k & IDX))] = park(S[j0 + e + d]);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (j0 + e < n) R[skew((int)(v[e].k & IDX))] = park(S[j0 + e]);
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (j0 + e < n) R[skew((int)(v[e].k & IDX))] = (uint32_t)(j0 + e + 1);
+                ranks_in_R = true;
+            }
         } else {
             const uint32_t prv_last = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
             uint32_t packed[E];
             bucket_run_bounds<E, LOG>(v, lane, n, nxt_first, prv_last, packed);
-            __syncwarp();
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 sw[skew(j0 + e)] = v[e].k;
@@ -414,39 +473,38 @@ qm_predict_tile_kernel(const PredictParams p) {
                 __syncwarp();
                 rank_exact64<E, SHIFT>(myX, n, xc, lane, R);
             }
+            ranks_in_R = true;
         }
         __syncwarp();
 
-        // ---- 3. fitted sorted values of this (cell, group) → shared memory (coalesced)
-        for (int j = lane; j < m; j += 32) myS[skew(j)] = S[j];
-        __syncwarp();
-
-        // ---- 4. rank → quantile → inverse CDF, value parked (float32) in place of the rank
-        {
+        if (ranks_in_R) {
+            // ---- 4. (ties, or T_pred != T_fit) rank → quantile → inverse CDF of the fitted values
+            for (int j = lane; j < m; j += 32) myS[skew(j)] = S[j];
+            __syncwarp();
             const double dn = pp_denominator(n), dm = pp_denominator(m);
             auto Sat = [&](int i) -> double { return (double)myS[skew(i)]; };
-#pragma unroll 2
             for (int j = j0; j < j1; ++j) {
                 const int rk = (int)R[skew(j)];
                 if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
-                R[skew(j)] = __float_as_uint((float)inverse_cdf_acc(rk, n, m, Sat, dn, dm));
+                R[skew(j)] = park((float)inverse_cdf_acc(rk, n, m, Sat, dn, dm));
             }
+            __syncwarp();
+        } else if (p.rank_out) {
+#pragma unroll
+            for (int e = 0; e < E; ++e)      // instrumentation only: rank of the member at sorted position pos
+                if (j0 + e < n) p.rank_out[(int64_t)rg[v[e].k & IDX] * p.ld_out + c] = j0 + e + 1;
         }
-        __syncwarp();
 
-        // ---- 5. output in member order (the fitted values are no longer needed: reuse their row)
+        // ---- 5. restore the shift (and remove the target climatology) in member order
         if (SHIFT) {
-            slide_window(myX, n, j0, j1, [&](int j, float, double sum) {
-                const double shift = div_count(sum, win_count(j, n)) - xc;
-                double res = shift + (double)__uint_as_float(R[skew(j)]);     // bcsd.py:263
-                if (p.return_anoms) res = res - yc;                           // bcsd.py:267
-                myS[skew(j)] = (float)res;
-            });
-        } else {
-            for (int j = j0; j < j1; ++j) {
-                const double val = (double)__uint_as_float(R[skew(j)]);
-                const double res = (p.mode == SDB_MODE_BCSD_P && p.return_anoms) ? val / yc : val;   // bcsd.py:170-185
-                myS[skew(j)] = (float)res;
+            uint32_t* rowR = R + skew(j0);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (j0 + e < n) {
+                    double res = (double)sh[e] + (double)__uint_as_float(rowR[e]);    // bcsd.py:263
+                    if (p.return_anoms) res = res - yc;                              // bcsd.py:267
+                    rowR[e] = __float_as_uint((float)res);
+                }
             }
         }
     }
@@ -457,7 +515,7 @@ qm_predict_tile_kernel(const PredictParams p) {
         const int64_t cs = c0 + cc;
         if (cs < p.C) {
             float* outp = (float*)p.out + cs;
-            const float* srcp = tileS + cc * NPS;
+            const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
 #pragma unroll 4
             for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT)
                 __stcs(outp + (int64_t)rg[j] * p.ld_out, srcp[skew(j)]);
