@@ -34,9 +34,11 @@ __device__ __forceinline__ int skew(int j) { return j + (j >> 5); }
 template <int E>
 constexpr size_t fit_tile_smem() { return (size_t)TILE_CT * TileGeom<E>::NPS * 4; }
 template <int E>
-constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 3 * TileGeom<E>::NPS * 4; }
+constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 2 * TileGeom<E>::NPS * 4; }
 
-// cooperative, coalesced load of one group's rows for the CTA's 8 cells into tile[cell][skew(j)]
+// cooperative, coalesced load of one group's rows for the CTA's 8 cells into tile[cell][skew(j)].
+// cp.async (LDGSTS): every thread fires all its row segments back to back, no register staging,
+// one wait at the end — the whole tile costs one memory latency instead of one per batch.
 template <int E>
 __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
                                           int64_t c0, const int32_t* __restrict__ rg, int n,
@@ -47,9 +49,17 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
     const bool ok = c < C && (!valid || valid[c]);
     float* dst = tile + cc * NPS;
     const float* col = src + c;
+    if (ok) {
 #pragma unroll 4
-    for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT)
-        dst[skew(j)] = ok ? __ldcs(col + (int64_t)rg[j] * ld) : 0.0f;
+        for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT) {
+            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst + skew(j));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(saddr), "l"(col + (int64_t)rg[j] * ld) : "memory");
+        }
+    } else {
+        for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT) dst[skew(j)] = 0.0f;
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
 // ---------------------------------------------------------------- fit
@@ -200,117 +210,52 @@ __device__ __forceinline__ void bucket_run_bounds(const K32 (&v)[E], int lane, i
 }
 
 // Out-of-line exact ranking of one (cell, group): 64-bit key + position sort (the generic
-// algorithm) for the rare group whose keys defeat the bucket quantisation (a long bucket holding
-// distinct keys).  Writes the 1-based tie-max rank of member j to R[skew(j)].
+// algorithm) for the rare group whose keys defeat the bucket quantisation (a bucket holding three
+// or more distinct keys).  Writes the 1-based tie-max rank of member j over the input row:
+// Xu[skew(j)] = rank (the inputs are not needed afterwards).
 template <int E, bool SHIFT>
-__device__ __noinline__ void rank_exact64(const float* myX, int n, double xc, int lane, uint32_t* R) {
+__device__ __noinline__ void rank_exact64(float* myX, int n, double xc, int lane) {
     K64I u[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int j = lane * E + e;
         u[e] = (j < n) ? make_rank_item64(exact_key<SHIFT>(myX, n, j, xc), (uint32_t)j) : sentinel_item<K64I>((uint32_t)j);
     }
+    __syncwarp();                                   // every lane has read what it needs from the row
     sort_blocked<K64I, E, 32>(u, lane, nullptr);
     int r2[E];
     tie_max_ranks<K64I, E, 32>(u, lane, r2, nullptr);
+    uint32_t* Xu = reinterpret_cast<uint32_t*>(myX);
 #pragma unroll
     for (int e = 0; e < E; ++e)
-        if (u[e].i < (uint32_t)n) R[skew((int)u[e].i)] = (uint32_t)r2[e];
+        if (u[e].i < (uint32_t)n) Xu[skew((int)u[e].i)] = (uint32_t)r2[e];
 }
 
-// Exact ranks when some bucket holds several members.  sw[] holds the sorted packed words
-// (bucket << LOG | member), R[] receives start | end << 10 | B << 21 per sorted position and,
-// at the end, the rank of member j at R[skew(j)].  Runtime loops over shared memory only.
-template <int E, int LOG, bool SHIFT>
-__device__ __noinline__ bool rank_with_ties(const float* myX, uint32_t* sw, uint32_t* R, int n, double xc, int lane) {
-    constexpr uint32_t IDX = (1u << LOG) - 1u;
-    const int p0 = lane * E, p1 = (p0 + E < n) ? p0 + E : n;
-    // bad pair (pos, pos+1): same bucket, different exact keys
-    uint32_t bm_bad = 0;
-    for (int pos = p0; pos < p1; ++pos) {
-        const uint32_t pk = R[skew(pos)];
-        const int en = (int)((pk >> 10) & 0x7ffu);
-        if (pos + 1 < en) {
-            const double a = exact_key<SHIFT>(myX, n, (int)(sw[skew(pos)] & IDX), xc);
-            const double b = exact_key<SHIFT>(myX, n, (int)(sw[skew(pos + 1)] & IDX), xc);
-            if (a != b) bm_bad |= 1u << (pos - p0);
-        }
-    }
-    if (!__any_sync(0xffffffffu, bm_bad != 0)) {
-        // multi-member buckets hold exact ties only: every member takes the end of its run
-        __syncwarp();
-        uint32_t rk[1];
-        (void)rk;
-        // ranks are scattered by member position; the run table is still needed by other lanes
-        // only through R[pos] of THEIR positions, so stage through sw (idx | rank << LOG)
-        for (int pos = p0; pos < p1; ++pos) {
-            const uint32_t en = (R[skew(pos)] >> 10) & 0x7ffu;
-            sw[skew(pos)] = (sw[skew(pos)] & IDX) | (en << LOG);
-        }
-        __syncwarp();
-        for (int pos = p0; pos < p1; ++pos) {
-            const uint32_t t = sw[skew(pos)];
-            R[skew((int)(t & IDX))] = t >> LOG;
-        }
-        return true;
-    }
-    // exclusive prefix count of bad pairs over sorted positions → B, packed into R[pos] bits 21..31
-    const int mine = __popc(bm_bad);
-    int incl = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const int before = incl - mine;
-    for (int pos = p0; pos < p1; ++pos) {
-        const uint32_t B = (uint32_t)(before + __popc(bm_bad & ((1u << (pos - p0)) - 1u)));
-        R[skew(pos)] |= B << 21;
-    }
-    __syncwarp();
-    bool need_fallback = false;
-    for (int pos = p0; pos < p1; ++pos) {
-        const uint32_t pk = R[skew(pos)];
-        const int s = (int)(pk & 0x3ffu), en = (int)((pk >> 10) & 0x7ffu);
-        const int L = en - s;
-        int r;
-        if (L == 1) r = pos + 1;
-        else {
-            const int nbad = (int)(R[skew(en - 1)] >> 21) - (int)(R[skew(s)] >> 21);
-            if (nbad == 0) r = en;
-            else if (L > TILE_LMAX) { need_fallback = true; r = en; }
-            else {
-                const double kp = exact_key<SHIFT>(myX, n, (int)(sw[skew(pos)] & IDX), xc);
-                int cnt = 0;
-                for (int q2 = s; q2 < en; ++q2)
-                    cnt += exact_key<SHIFT>(myX, n, (int)(sw[skew(q2)] & IDX), xc) <= kp ? 1 : 0;
-                r = s + cnt;
-            }
-        }
-        // members keep their identity in the low bits, so other lanes may still read sw[pos] & IDX
-        sw[skew(pos)] = (sw[skew(pos)] & IDX) | ((uint32_t)r << LOG);
-    }
-    __syncwarp();
-    if (__any_sync(0xffffffffu, need_fallback)) return false;
-    for (int pos = p0; pos < p1; ++pos) {
-        const uint32_t t = sw[skew(pos)];
-        R[skew((int)(t & IDX))] = t >> LOG;
-    }
-    return true;
+// three-way exact comparison of the rank keys of members a and b: -1, 0, +1
+template <bool SHIFT>
+__device__ __noinline__ int cmp_members(const float* myX, int n, int a, int b, double xc) {
+    const double ka = exact_key<SHIFT>(myX, n, a, xc), kb = exact_key<SHIFT>(myX, n, b, xc);
+    return ka < kb ? -1 : (ka > kb ? 1 : 0);
+}
+
+// mapped value of 1-based rank rk: the fitted order statistic itself when the lengths agree,
+// else the Cunnane interpolation / OLS tails, read from the state record in global memory
+static __device__ __noinline__ float mapped_value_general(const float* __restrict__ S, int rk, int n, int m) {
+    auto Sat = [&](int i) -> double { return (double)__ldg(S + i); };
+    return (float)inverse_cdf_acc(rk, n, m, Sat, pp_denominator(n), pp_denominator(m));
 }
 
 // ---------------------------------------------------------------- predict
 template <int E, bool SHIFT>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
+__global__ void __launch_bounds__(TILE_THREADS, 3)
 qm_predict_tile_kernel(const PredictParams p) {
     using G = TileGeom<E>;
     constexpr int NPS = G::NPS, LOG = G::LOG;
     constexpr uint32_t QMAX = G::QMAX;
     constexpr uint32_t IDX = (1u << LOG) - 1u;
     extern __shared__ uint32_t smem_u[];
-    float* tileX = reinterpret_cast<float*>(smem_u);                  // inputs of the group
-    float* tileS = tileX + TILE_CT * NPS;                             // (slow path) sorted words → fitted values
-    uint32_t* tileR = reinterpret_cast<uint32_t*>(tileS + TILE_CT * NPS);   // (run table →) ranks/values → outputs
+    float* tileX = reinterpret_cast<float*>(smem_u);                        // inputs of the group
+    uint32_t* tileR = smem_u + TILE_CT * NPS;                               // shift → outputs (float bits)
 
     const int g = blockIdx.y;
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
@@ -322,11 +267,10 @@ qm_predict_tile_kernel(const PredictParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = c0 + warp;
     float* myX = tileX + warp * NPS;
-    float* myS = tileS + warp * NPS;
-    uint32_t* sw = reinterpret_cast<uint32_t*>(myS);
     uint32_t* R = tileR + warp * NPS;
     const int j0 = lane * E;
     const int j1 = (j0 + E < n) ? j0 + E : n;
+    const int rb = skew(j0);
     const bool in_range = c < p.C;
     const bool active = in_range && (!p.valid || p.valid[c]);
 
@@ -340,12 +284,26 @@ qm_predict_tile_kernel(const PredictParams p) {
         if (SHIFT) xc = (double)((const float*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
         if (p.mode != SDB_MODE_QM && p.return_anoms) yc = (double)((const float*)p.y_climo)[(int64_t)sg * p.ld_climo + c];
         const bool ratio = (p.mode == SDB_MODE_BCSD_P) && p.return_anoms;
+        const bool same = (n == m);
+
+        // final value of a member from its mapped value: restore the shift parked in R (float32)
+        // and remove the target climatology (bcsd.py:263,267 / 170-185)
+        auto finish = [&](int member, float val) {
+            double res;
+            if (SHIFT) {
+                res = (double)__uint_as_float(R[skew(member)]) + (double)val;
+                if (p.return_anoms) res = res - yc;
+            } else {
+                res = ratio ? (double)val / yc : (double)val;
+            }
+            R[skew(member)] = __float_as_uint((float)res);
+        };
 
         // ---- 1. own members (+ 4 / 5 halo) to registers; key bounds from the plain value range
         constexpr int HL = SHIFT ? 4 : 0, HR = SHIFT ? 5 : 0;
-        float xh[E + HL + HR];
+        K32 v[E];
         {
-            const int rb = skew(j0);
+            float xh[E + HL + HR];
 #pragma unroll
             for (int i = 0; i < E + HL + HR; ++i) {
                 const int e = i - HL;                          // member offset inside / around the lane's block
@@ -354,63 +312,59 @@ qm_predict_tile_kernel(const PredictParams p) {
                 const int addr = (E == 32) ? rb + e + (e < 0 ? -1 : (e >= 32 ? 1 : 0)) : skew(jj < 0 ? 0 : jj);
                 xh[i] = (jj >= 0 && jj < n) ? myX[addr] : 0.0f;
             }
-        }
-        float lo32 = INFINITY, hi32 = -INFINITY;
-        bool bad = false;
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if (j0 + e < n) {
-                const float x = xh[e + HL];
-                lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x);
-                bad |= !isfinite(x);
-            }
-        }
-        if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
-        lo32 = warp_min(lo32); hi32 = warp_max(hi32);
-
-        // ---- 2. exact rank keys → monotone bucket number, packed with the member position.
-        // Bounds are a guess (value range + 1/8 margin, centred on the climatology for the shifted
-        // key); out-of-range keys clamp to the end buckets, which keeps the map monotone — the
-        // exact fix-up below sorts out whatever shares a bucket.
-        K32 v[E];
-        float sh[SHIFT ? E : 1];
-        if (SHIFT) {
-            const double range = (double)hi32 - (double)lo32;
-            const double lo = (double)lo32 - 0.125 * range, hi = (double)hi32 + 0.125 * range;
-            const double scale = (hi > lo && isfinite(hi - lo)) ? (double)(QMAX - 1) / (hi - lo) : 0.0;
-            double sum = 0.0;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) sum += (double)xh[i];
+            float lo32 = INFINITY, hi32 = -INFINITY;
+            bool bad = false;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int j = j0 + e;
-                if (j < n) {
-                    const double shift = div_count(sum, win_count(j, n)) - xc;
-                    const double t = (((double)xh[e + 4] - shift) - lo) * scale;
-                    uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
-                    q = q > QMAX - 1 ? QMAX - 1 : q;
-                    v[e].k = (q << LOG) | (uint32_t)j;
-                    sh[e] = (float)shift;
-                } else {
-                    v[e].k = 0xffffffffu;
-                    sh[e] = 0.0f;
+                if (j0 + e < n) {
+                    const float x = xh[e + HL];
+                    lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x);
+                    bad |= !isfinite(x);
                 }
-                sum += (double)xh[e + 9];
-                sum -= (double)xh[e];
             }
-        } else {
-            const float range = hi32 - lo32;
-            const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
+            if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
+            lo32 = warp_min(lo32); hi32 = warp_max(hi32);
+
+            // ---- 2. exact rank keys → monotone bucket number, packed with the member position.
+            // The bounds are a guess (value range + 1/8 margin); keys outside clamp to the end
+            // buckets, which keeps the map monotone — whatever shares a bucket is compared exactly.
+            if (SHIFT) {
+                const double range = (double)hi32 - (double)lo32;
+                const double lo = (double)lo32 - 0.125 * range, hi = (double)hi32 + 0.125 * range;
+                const double scale = (hi > lo && isfinite(hi - lo)) ? (double)(QMAX - 1) / (hi - lo) : 0.0;
+                double sum = 0.0;
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int j = j0 + e;
-                if (j < n) {
-                    const float t = (xh[e] - lo32) * scale;
-                    uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
-                    q = q > QMAX - 1 ? QMAX - 1 : q;
-                    v[e].k = (q << LOG) | (uint32_t)j;
-                } else {
-                    v[e].k = 0xffffffffu;
+                for (int i = 0; i < 9; ++i) sum += (double)xh[i];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int j = j0 + e;
+                    if (j < n) {
+                        const double shift = div_count(sum, win_count(j, n)) - xc;
+                        const double t = (((double)xh[e + 4] - shift) - lo) * scale;
+                        uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
+                        q = q > QMAX - 1 ? QMAX - 1 : q;
+                        v[e].k = (q << LOG) | (uint32_t)j;
+                        R[rb + e] = __float_as_uint((float)shift);
+                    } else {
+                        v[e].k = 0xffffffffu;
+                    }
+                    sum += (double)xh[e + 9];
+                    sum -= (double)xh[e];
+                }
+            } else {
+                const float range = hi32 - lo32;
+                const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int j = j0 + e;
+                    if (j < n) {
+                        const float t = (xh[e] - lo32) * scale;
+                        uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
+                        q = q > QMAX - 1 ? QMAX - 1 : q;
+                        v[e].k = (q << LOG) | (uint32_t)j;
+                    } else {
+                        v[e].k = 0xffffffffu;
+                    }
                 }
             }
         }
@@ -418,98 +372,92 @@ qm_predict_tile_kernel(const PredictParams p) {
         // ---- 3. one 32-bit keys-only sort
         sort_blocked<K32, E, 32>(v, lane, nullptr);
         const uint32_t nxt_first = __shfl_down_sync(0xffffffffu, v[0].k, 1);
-        bool any_eq = false;
+        uint32_t bm_eq = 0;                       // bit e: sorted positions (pos, pos+1) share a bucket
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-            any_eq |= (j0 + e + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG));
+            bm_eq |= ((j0 + e + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG))) ? (1u << e) : 0u;
         }
-        const bool same = (n == m);
-        bool ranks_in_R = false;        // false: R[member] already holds the mapped value (float bits)
-        auto park = [&](float val) -> uint32_t { return __float_as_uint(ratio ? (float)((double)val / yc) : val); };
+        __syncwarp();                             // shifts parked in R are visible to every lane
 
-        if (!__any_sync(0xffffffffu, any_eq)) {
-            if (same) {
-                // one member per bucket, same length: the member at sorted position pos takes the
-                // fitted order statistic S[pos] — read straight from the state record
-                const bool vec = ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
-                if (vec && E % 4 == 0) {
+        // ---- 4. (member, rank) of every sorted position → mapped value → output
+        // mode 0: rank = position + 1.  mode 1: buckets with exact ties only → run ends.
+        // mode 2: isolated pairs sharing a bucket, fixed by one exact comparison each.
+        // mode 3: anything else → exact 64-bit sort of the group.
+        int mode = 0;
+        uint32_t bm_gt = 0, bm_tie = 0;           // bit e: pair (pos, pos+1) is inverted / exactly tied
+        uint32_t prev_gt = 0, prev_tie = 0;       // the same for the pair (j0 - 1, j0) owned by the previous lane
+        if (__any_sync(0xffffffffu, bm_eq != 0)) {
 #pragma unroll
-                    for (int e = 0; e < E; e += 4) {
-                        if (j0 + e + 3 < n) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(S + j0 + e);
-                            R[skew((int)(v[e].k & IDX))] = park(s4.x);
-                            R[skew((int)(v[e + 1].k & IDX))] = park(s4.y);
-                            R[skew((int)(v[e + 2].k & IDX))] = park(s4.z);
-                            R[skew((int)(v[e + 3].k & IDX))] = park(s4.w);
-                        } else {
-#pragma unroll
-                            for (int d = 0; d < 4; ++d)
-                                if (j0 + e + d < n) R[skew((int)(v[e + d].k & IDX))] = park(S[j0 + e + d]);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < E; ++e)
-                        if (j0 + e < n) R[skew((int)(v[e].k & IDX))] = park(S[j0 + e]);
+            for (int e = 0; e < E; ++e) {
+                if ((bm_eq >> e) & 1u) {
+                    const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
+                    const int cmp = cmp_members<SHIFT>(myX, n, (int)(v[e].k & IDX), (int)(kn & IDX), xc);
+                    bm_gt |= (cmp > 0) ? (1u << e) : 0u;
+                    bm_tie |= (cmp == 0) ? (1u << e) : 0u;
                 }
-            } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e)
-                    if (j0 + e < n) R[skew((int)(v[e].k & IDX))] = (uint32_t)(j0 + e + 1);
-                ranks_in_R = true;
+            }
+            const bool all_ties = !__any_sync(0xffffffffu, (bm_eq & ~bm_tie) != 0);
+            const uint32_t nxt_eq0 = __shfl_down_sync(0xffffffffu, bm_eq & 1u, 1);
+            const bool long_run = ((bm_eq & (bm_eq >> 1)) != 0) || ((lane < 31) && (bm_eq >> (E - 1) & 1u) && nxt_eq0);
+            mode = all_ties ? 1 : (__any_sync(0xffffffffu, long_run) ? 3 : 2);
+            prev_gt = __shfl_up_sync(0xffffffffu, (bm_gt >> (E - 1)) & 1u, 1);
+            prev_tie = __shfl_up_sync(0xffffffffu, (bm_tie >> (E - 1)) & 1u, 1);
+            if (lane == 0) { prev_gt = 0; prev_tie = 0; }
+        }
+
+        if (mode == 3) {
+            rank_exact64<E, SHIFT>(myX, n, xc, lane);            // ranks by member → input row
+            __syncwarp();
+            const uint32_t* Xu = reinterpret_cast<const uint32_t*>(myX);
+            for (int j = j0; j < j1; ++j) {
+                const int rk = (int)Xu[skew(j)];
+                if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
+                finish(j, same ? __ldg(S + rk - 1) : mapped_value_general(S, rk, n, m));
             }
         } else {
-            const uint32_t prv_last = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
-            uint32_t packed[E];
-            bucket_run_bounds<E, LOG>(v, lane, n, nxt_first, prv_last, packed);
+            uint32_t run_end[(E > 1) ? E : 1];
+            if (mode == 1) {
+                const uint32_t prv_last = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
+                uint32_t packed[E];
+                bucket_run_bounds<E, LOG>(v, lane, n, nxt_first, prv_last, packed);
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                sw[skew(j0 + e)] = v[e].k;
-                R[skew(j0 + e)] = packed[e];
+                for (int e = 0; e < E; ++e) run_end[e] = packed[e] >> 10;
             }
-            __syncwarp();
-            if (!rank_with_ties<E, LOG, SHIFT>(myX, sw, R, n, xc, lane)) {
-                __syncwarp();
-                rank_exact64<E, SHIFT>(myX, n, xc, lane, R);
-            }
-            ranks_in_R = true;
-        }
-        __syncwarp();
-
-        if (ranks_in_R) {
-            // ---- 4. (ties, or T_pred != T_fit) rank → quantile → inverse CDF of the fitted values
-            for (int j = lane; j < m; j += 32) myS[skew(j)] = S[j];
-            __syncwarp();
-            const double dn = pp_denominator(n), dm = pp_denominator(m);
-            auto Sat = [&](int i) -> double { return (double)myS[skew(i)]; };
-            for (int j = j0; j < j1; ++j) {
-                const int rk = (int)R[skew(j)];
-                if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
-                R[skew(j)] = park((float)inverse_cdf_acc(rk, n, m, Sat, dn, dm));
-            }
-            __syncwarp();
-        } else if (p.rank_out) {
+            const uint32_t prv_last_k = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
+            if (same || !(p.rank_out == nullptr && false)) {
 #pragma unroll
-            for (int e = 0; e < E; ++e)      // instrumentation only: rank of the member at sorted position pos
-                if (j0 + e < n) p.rank_out[(int64_t)rg[v[e].k & IDX] * p.ld_out + c] = j0 + e + 1;
-        }
-
-        // ---- 5. restore the shift (and remove the target climatology) in member order
-        if (SHIFT) {
-            uint32_t* rowR = R + skew(j0);
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if (j0 + e < n) {
-                    double res = (double)sh[e] + (double)__uint_as_float(rowR[e]);    // bcsd.py:263
-                    if (p.return_anoms) res = res - yc;                              // bcsd.py:267
-                    rowR[e] = __float_as_uint((float)res);
+                for (int e = 0; e < E; ++e) {
+                    const int pos = j0 + e;
+                    if (pos < n) {
+                        int member = (int)(v[e].k & IDX);
+                        int rk = pos + 1;
+                        if (mode == 1) {
+                            rk = (int)run_end[e];
+                        } else if (mode == 2) {
+                            const uint32_t gt_here = (bm_gt >> e) & 1u, tie_here = (bm_tie >> e) & 1u;
+                            const uint32_t gt_prev = (e == 0) ? prev_gt : (bm_gt >> (e == 0 ? 0 : e - 1)) & 1u;
+                            if (gt_here) {                       // inverted pair: this position takes the next member
+                                const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
+                                member = (int)(kn & IDX);
+                            } else if (gt_prev) {                // ... and the next position takes this one
+                                const uint32_t kp = (e == 0) ? prv_last_k : v[e == 0 ? e : e - 1].k;
+                                member = (int)(kp & IDX);
+                            }
+                            if (tie_here) rk = pos + 2;          // exact tie: both take the higher rank
+                        }
+                        if (p.rank_out) p.rank_out[(int64_t)rg[member] * p.ld_out + c] = rk;
+                        float val;
+                        if (same) val = __ldg(S + rk - 1);
+                        else      val = mapped_value_general(S, rk, n, m);
+                        finish(member, val);
+                    }
                 }
             }
         }
     }
     __syncthreads();
-    // ---- 6. coalesced store of the tile (rows of 8 cells)
+    // ---- 5. coalesced store of the tile (rows of 8 cells)
     {
         const int cc = threadIdx.x & (TILE_CT - 1);
         const int64_t cs = c0 + cc;
