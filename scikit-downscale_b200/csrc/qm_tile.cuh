@@ -261,28 +261,34 @@ qm_predict_tile_kernel(const PredictParams p) {
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
     const int n = p.len[g];
     const int32_t* rg = p.rows + (int64_t)g * p.max_len;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = c0 + warp;
+    const bool in_range = c < p.C;
+    const bool active = in_range && (!p.valid || p.valid[c]);
+    // per-(cell, group) scalars: fetched before the tile load so their latency hides behind it
+    const int sg = p.state_gid[g];
+    const int m = p.fit_len[sg];
+    const float* S = (const float*)p.state + (active ? c : 0) * p.state_ld + p.state_off[sg];
+    float xc_f = 0.0f, yc_f = 0.0f;
+    if (active) {
+        if (SHIFT) xc_f = ((const float*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
+        if (p.mode != SDB_MODE_QM && p.return_anoms) yc_f = ((const float*)p.y_climo)[(int64_t)sg * p.ld_climo + c];
+        // the fitted sorted values are wanted right after the sort: pull the record into L2 now
+        if (lane * 32 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(S + lane * 32));
+    }
     load_tile<E>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid);
     __syncthreads();
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t c = c0 + warp;
     float* myX = tileX + warp * NPS;
     uint32_t* R = tileR + warp * NPS;
     const int j0 = lane * E;
     const int j1 = (j0 + E < n) ? j0 + E : n;
     const int rb = skew(j0);
-    const bool in_range = c < p.C;
-    const bool active = in_range && (!p.valid || p.valid[c]);
 
     if (in_range && !active) {
         for (int j = lane; j < n; j += 32) R[skew(j)] = __float_as_uint(NAN);
     } else if (active) {
-        const int sg = p.state_gid[g];
-        const int m = p.fit_len[sg];
-        const float* S = (const float*)p.state + c * p.state_ld + p.state_off[sg];
-        double xc = 0.0, yc = 0.0;
-        if (SHIFT) xc = (double)((const float*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
-        if (p.mode != SDB_MODE_QM && p.return_anoms) yc = (double)((const float*)p.y_climo)[(int64_t)sg * p.ld_climo + c];
+        const double xc = (double)xc_f, yc = (double)yc_f;
         const bool ratio = (p.mode == SDB_MODE_BCSD_P) && p.return_anoms;
         const bool same = (n == m);
 
@@ -406,7 +412,30 @@ qm_predict_tile_kernel(const PredictParams p) {
             if (lane == 0) { prev_gt = 0; prev_tie = 0; }
         }
 
-        if (mode == 3) {
+        if (mode == 0 && same && !p.rank_out && (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0)) {
+            // the common case: one member per bucket, same length — the member at sorted position
+            // pos takes the fitted order statistic S[pos]; the lane's 32 values are 8 vector loads
+            float4 s4[E / 4];
+#pragma unroll
+            for (int q4 = 0; q4 < E / 4; ++q4) {
+                const int pos = j0 + 4 * q4;
+                if (pos + 3 < n) s4[q4] = __ldg(reinterpret_cast<const float4*>(S + pos));
+                else {
+                    s4[q4].x = pos < n ? __ldg(S + pos) : 0.0f;
+                    s4[q4].y = pos + 1 < n ? __ldg(S + pos + 1) : 0.0f;
+                    s4[q4].z = pos + 2 < n ? __ldg(S + pos + 2) : 0.0f;
+                    s4[q4].w = 0.0f;
+                }
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < E / 4; ++q4) {
+                const int pos = j0 + 4 * q4;
+                if (pos < n) finish((int)(v[4 * q4].k & IDX), s4[q4].x);
+                if (pos + 1 < n) finish((int)(v[4 * q4 + 1].k & IDX), s4[q4].y);
+                if (pos + 2 < n) finish((int)(v[4 * q4 + 2].k & IDX), s4[q4].z);
+                if (pos + 3 < n) finish((int)(v[4 * q4 + 3].k & IDX), s4[q4].w);
+            }
+        } else if (mode == 3) {
             rank_exact64<E, SHIFT>(myX, n, xc, lane);            // ranks by member → input row
             __syncwarp();
             const uint32_t* Xu = reinterpret_cast<const uint32_t*>(myX);
@@ -425,7 +454,7 @@ qm_predict_tile_kernel(const PredictParams p) {
                 for (int e = 0; e < E; ++e) run_end[e] = packed[e] >> 10;
             }
             const uint32_t prv_last_k = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
-            if (same || !(p.rank_out == nullptr && false)) {
+            {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int pos = j0 + e;

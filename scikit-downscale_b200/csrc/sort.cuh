@@ -74,7 +74,10 @@ __device__ __forceinline__ void cmpswap(I& a, I& b) {
 }
 // keep the smaller (lower==true) or the larger of own item v and partner item o
 __device__ __forceinline__ K32 keep(const K32& v, const K32& o, bool lower) {
-    K32 r; r.k = lower ? min(v.k, o.k) : max(v.k, o.k); return r;
+    K32 r;
+    r.k = min(v.k, o.k);                 // min, then a predicated max over it: two VIMNMX, no select
+    if (!lower) r.k = max(v.k, o.k);
+    return r;
 }
 template <class I>
 __device__ __forceinline__ I keep(const I& v, const I& o, bool lower) {
