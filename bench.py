@@ -257,6 +257,27 @@ def run_b200(a):
     value = world * C * T / (ms_step * 1e-3)
     model._state.check_finite()
 
+    # ---- the only collective of the path: gather of the predicted field (reported separately)
+    gather = None
+    if world > 1:
+        from skdownscale_b200.distributed import gather_cells
+        fullf = gather_cells(out, world * C)          # warm-up (NCCL communicator setup)
+        del fullf
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        fullf = gather_cells(out, world * C)
+        g1.record()
+        barrier()
+        gms = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        recv = (world - 1) * T * C * 4
+        gather = {'ms': float(gms.item()), 'bytes_received_per_gpu': recv,
+                  'GB/s_per_gpu': recv / (float(gms.item()) * 1e-3) / 1e9,
+                  'what': 'NCCL all-gather of the predicted field [T, cells] + local re-interleave to cell-fastest layout'}
+        del fullf
+        torch.cuda.empty_cache()
+
     # ---- end to end through the public API: pinned host inputs, H2D + fit + predict + D2H per step
     e2e = None
     if not a.no_e2e:
@@ -307,8 +328,9 @@ def run_b200(a):
                        'l2': 'inputs 17 GB/GPU >> 126 MB L2 (no flush needed)'},
             'clocks': clocks,
             'e2e': e2e,
+            'gather': gather,
             'gpu_launches': 4 * a.steps,
-            'roofline': {'bound': 'hbm', 'kernel': 'qm_predict_kernel (dominant)', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+            'roofline': {'bound': 'hbm', 'kernel': 'qm_predict_tile_kernel<32,true> (dominant)', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                          'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
                          'algorithmic_bytes_per_cell_timestep': ALG_BYTES_PREDICT, 'kernel_ms': pms,
                          'whole_step': {'achieved': ach_step, 'frac': ach_step / peak,
