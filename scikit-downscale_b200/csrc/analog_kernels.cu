@@ -209,7 +209,7 @@ analog_kernel(const AnalogParams a) {
     int bi[KL];
 #pragma unroll
     for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) { bd[i] = INFINITY; bi[i] = -1; }
-    if (KREG == 0) for (int i = 0; i < k; ++i) { bd[i] = INFINITY; bi[i] = -1; }
+    if (KREG == 0) for (int i = 0; i < k; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
     double worst = INFINITY;                          // current k-th best distance
 
     for (int t0 = 0; t0 < a.t_fit; t0 += AN_CHUNK) {
@@ -248,15 +248,46 @@ analog_kernel(const AnalogParams a) {
                     for (int i = 0; i < KREG; ++i) if (i == k - 1) w = bd[i];
                     worst = w;
                 } else {
-                    int i = k - 1;
-                    while (i > 0 && d < bd[i - 1]) { bd[i] = bd[i - 1]; bi[i] = bi[i - 1]; --i; }
-                    bd[i] = d; bi[i] = id;
-                    worst = bd[k - 1];
+                    // large k: binary max-heap on (distance, index) in local memory — O(log k) per accepted
+                    // point instead of shifting a sorted list.  d < root is strict, so a later point at
+                    // the same distance never evicts an earlier one (lowest index first on ties).
+                    int pos = 0;
+                    while (true) {
+                        const int l = 2 * pos + 1;
+                        if (l >= k) break;
+                        const int r = l + 1;
+                        int big = l;
+                        if (r < k && (bd[l] < bd[r] || (bd[l] == bd[r] && bi[l] < bi[r]))) big = r;
+                        if (!(d < bd[big] || (d == bd[big] && id < bi[big]))) break;
+                        bd[pos] = bd[big]; bi[pos] = bi[big];
+                        pos = big;
+                    }
+                    bd[pos] = d; bi[pos] = id;
+                    worst = bd[0];
                 }
             }
         }
     }
     if (!live) return;
+    if (KREG == 0) {
+        // heap → ascending (distance, index) order, in place
+        for (int end = k - 1; end > 0; --end) {
+            const double d = bd[end]; const int id = bi[end];
+            bd[end] = bd[0]; bi[end] = bi[0];
+            int pos = 0;
+            while (true) {
+                const int l = 2 * pos + 1;
+                if (l >= end) break;
+                const int r = l + 1;
+                int big = l;
+                if (r < end && (bd[l] < bd[r] || (bd[l] == bd[r] && bi[l] < bi[r]))) big = r;
+                if (!(d < bd[big] || (d == bd[big] && id < bi[big]))) break;
+                bd[pos] = bd[big]; bi[pos] = bi[big];
+                pos = big;
+            }
+            bd[pos] = d; bi[pos] = id;
+        }
+    }
     if (a.knn_idx) {
         if (KREG > 0) {
 #pragma unroll

@@ -168,47 +168,6 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
-// run [start, end) of equal-bucket sorted positions around every position, packed
-// start | end << 10 (blocked layout, first n positions real).  O(1) per position: boundary
-// bitmaps per lane + one ballot each way.
-template <int E, int LOG>
-__device__ __forceinline__ void bucket_run_bounds(const K32 (&v)[E], int lane, int n, uint32_t nxt_first,
-                                                  uint32_t prv_last, uint32_t (&packed)[E]) {
-    uint32_t bm_last = 0, bm_first = 0;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int p = lane * E + e;
-        const uint32_t q = v[e].k >> LOG;
-        const uint32_t qn = ((e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k) >> LOG;
-        const uint32_t qp = ((e == 0) ? prv_last : v[e == 0 ? e : e - 1].k) >> LOG;
-        const bool last = (p >= n - 1) || (q != qn);
-        const bool first = (p == 0) || (p >= n) || (q != qp);
-        bm_last |= last ? (1u << e) : 0u;
-        bm_first |= first ? (1u << e) : 0u;
-    }
-    const int base = lane * E;
-    const int minb = base + __ffs(bm_last);                          // nearest run end at/after the lane start
-    const uint32_t has_l = __ballot_sync(0xffffffffu, bm_last != 0);
-    const uint32_t higher = (lane == 31) ? 0u : (has_l & ~((2u << lane) - 1u));
-    const int carry_e = __shfl_sync(0xffffffffu, minb, higher ? (__ffs(higher) - 1) : lane);
-    const int maxf = base + (31 - __clz(bm_first | 1u));             // nearest run start at/before the lane end
-    const uint32_t has_f = __ballot_sync(0xffffffffu, bm_first != 0);
-    const uint32_t lower = has_f & ((1u << lane) - 1u);
-    const int carry_s = __shfl_sync(0xffffffffu, maxf, lower ? (31 - __clz(lower)) : lane);
-    int cur = carry_e;
-#pragma unroll
-    for (int e = E - 1; e >= 0; --e) {
-        if ((bm_last >> e) & 1u) cur = base + e + 1;
-        packed[e] = (uint32_t)cur << 10;
-    }
-    cur = carry_s;
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        if ((bm_first >> e) & 1u) cur = base + e;
-        packed[e] |= (uint32_t)cur;
-    }
-}
-
 // Out-of-line exact ranking of one (cell, group): 64-bit key + position sort (the generic
 // algorithm) for the rare group whose keys defeat the bucket quantisation (a bucket holding three
 // or more distinct keys).  Writes the 1-based tie-max rank of member j over the input row:
@@ -232,9 +191,14 @@ __device__ __noinline__ void rank_exact64(float* myX, int n, double xc, int lane
 }
 
 // three-way exact comparison of the rank keys of members a and b: -1, 0, +1
+static __device__ __noinline__ int cmp_members_shift(const float* myX, int n, int a, int b, double xc) {
+    const double ka = window_key(myX, n, a, xc), kb = window_key(myX, n, b, xc);
+    return ka < kb ? -1 : (ka > kb ? 1 : 0);
+}
 template <bool SHIFT>
-__device__ __noinline__ int cmp_members(const float* myX, int n, int a, int b, double xc) {
-    const double ka = exact_key<SHIFT>(myX, n, a, xc), kb = exact_key<SHIFT>(myX, n, b, xc);
+__device__ __forceinline__ int cmp_members(const float* myX, int n, int a, int b, double xc) {
+    if (SHIFT) return cmp_members_shift(myX, n, a, b, xc);
+    const float ka = myX[skew(a)], kb = myX[skew(b)];          // the inputs themselves are the keys (-0 == +0)
     return ka < kb ? -1 : (ka > kb ? 1 : 0);
 }
 
@@ -387,12 +351,14 @@ qm_predict_tile_kernel(const PredictParams p) {
         __syncwarp();                             // shifts parked in R are visible to every lane
 
         // ---- 4. (member, rank) of every sorted position → mapped value → output
-        // mode 0: rank = position + 1.  mode 1: buckets with exact ties only → run ends.
-        // mode 2: isolated pairs sharing a bucket, fixed by one exact comparison each.
-        // mode 3: anything else → exact 64-bit sort of the group.
+        // mode 0: one member per bucket, rank = position + 1.
+        // mode 2: members sharing a bucket are compared exactly; runs of exact ties take the run end
+        //         (tie-max rank), an isolated inverted pair is swapped.
+        // mode 3: any other structure (3+ distinct keys in a bucket) → exact 64-bit sort of the group.
         int mode = 0;
         uint32_t bm_gt = 0, bm_tie = 0;           // bit e: pair (pos, pos+1) is inverted / exactly tied
-        uint32_t prev_gt = 0, prev_tie = 0;       // the same for the pair (j0 - 1, j0) owned by the previous lane
+        uint32_t prev_gt = 0;                     // the pair (j0 - 1, j0) owned by the previous lane is inverted
+        int tie_carry = 0;                        // rank of a tie run that continues past this lane's last member
         if (__any_sync(0xffffffffu, bm_eq != 0)) {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
@@ -403,14 +369,30 @@ qm_predict_tile_kernel(const PredictParams p) {
                     bm_tie |= (cmp == 0) ? (1u << e) : 0u;
                 }
             }
-            const bool all_ties = !__any_sync(0xffffffffu, (bm_eq & ~bm_tie) != 0);
+            // a non-tied same-bucket pair must be isolated: no other same-bucket pair touching it
+            const uint32_t nontie = bm_eq & ~bm_tie;
             const uint32_t nxt_eq0 = __shfl_down_sync(0xffffffffu, bm_eq & 1u, 1);
-            const bool long_run = ((bm_eq & (bm_eq >> 1)) != 0) || ((lane < 31) && (bm_eq >> (E - 1) & 1u) && nxt_eq0);
-            mode = all_ties ? 1 : (__any_sync(0xffffffffu, long_run) ? 3 : 2);
+            const uint32_t prv_eqL = __shfl_up_sync(0xffffffffu, (bm_eq >> (E - 1)) & 1u, 1);
+            uint32_t touching = (bm_eq << 1) | (bm_eq >> 1);
+            if (lane > 0 && prv_eqL) touching |= 1u;
+            if (lane < 31 && nxt_eq0) touching |= 1u << (E - 1);
+            mode = __any_sync(0xffffffffu, (nontie & touching) != 0) ? 3 : 2;
             prev_gt = __shfl_up_sync(0xffffffffu, (bm_gt >> (E - 1)) & 1u, 1);
-            prev_tie = __shfl_up_sync(0xffffffffu, (bm_tie >> (E - 1)) & 1u, 1);
-            if (lane == 0) { prev_gt = 0; prev_tie = 0; }
+            if (lane == 0) prev_gt = 0;
+            // tie runs: a position's rank is 1 + the first position at/after it whose tie bit is clear
+            const uint32_t emask = (E == 32) ? 0xffffffffu : ((1u << (E & 31)) - 1u);
+            const uint32_t open = ~bm_tie & emask;                 // bit e clear in bm_tie → run ends at pos
+            const int first_end = j0 + __ffs(open);               // 1-based rank of the first run end in this lane
+            const uint32_t has = __ballot_sync(0xffffffffu, open != 0);
+            const uint32_t higher = (lane == 31) ? 0u : (has & ~((2u << lane) - 1u));
+            tie_carry = __shfl_sync(0xffffffffu, first_end, higher ? (__ffs(higher) - 1) : lane);
         }
+        // rank of sorted position j0 + e under the tie-max rule
+        auto tie_rank = [&](int e) -> int {
+            const uint32_t emask = (E == 32) ? 0xffffffffu : ((1u << (E & 31)) - 1u);
+            const uint32_t open = (~bm_tie & emask) >> e;
+            return open ? (j0 + e + __ffs(open)) : tie_carry;
+        };
 
         if (mode == 0 && same && !p.rank_out && (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0)) {
             // the common case: one member per bucket, same length — the member at sorted position
@@ -445,14 +427,6 @@ qm_predict_tile_kernel(const PredictParams p) {
                 finish(j, same ? __ldg(S + rk - 1) : mapped_value_general(S, rk, n, m));
             }
         } else {
-            uint32_t run_end[(E > 1) ? E : 1];
-            if (mode == 1) {
-                const uint32_t prv_last = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
-                uint32_t packed[E];
-                bucket_run_bounds<E, LOG>(v, lane, n, nxt_first, prv_last, packed);
-#pragma unroll
-                for (int e = 0; e < E; ++e) run_end[e] = packed[e] >> 10;
-            }
             const uint32_t prv_last_k = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
             {
 #pragma unroll
@@ -461,10 +435,8 @@ qm_predict_tile_kernel(const PredictParams p) {
                     if (pos < n) {
                         int member = (int)(v[e].k & IDX);
                         int rk = pos + 1;
-                        if (mode == 1) {
-                            rk = (int)run_end[e];
-                        } else if (mode == 2) {
-                            const uint32_t gt_here = (bm_gt >> e) & 1u, tie_here = (bm_tie >> e) & 1u;
+                        if (mode == 2) {
+                            const uint32_t gt_here = (bm_gt >> e) & 1u;
                             const uint32_t gt_prev = (e == 0) ? prev_gt : (bm_gt >> (e == 0 ? 0 : e - 1)) & 1u;
                             if (gt_here) {                       // inverted pair: this position takes the next member
                                 const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
@@ -473,7 +445,7 @@ qm_predict_tile_kernel(const PredictParams p) {
                                 const uint32_t kp = (e == 0) ? prv_last_k : v[e == 0 ? e : e - 1].k;
                                 member = (int)(kp & IDX);
                             }
-                            if (tie_here) rk = pos + 2;          // exact tie: both take the higher rank
+                            rk = tie_rank(e);                    // exact ties: everyone takes the end of the run
                         }
                         if (p.rank_out) p.rank_out[(int64_t)rg[member] * p.ld_out + c] = rk;
                         float val;
