@@ -50,6 +50,7 @@ def parse():
     ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target CPU time of the cpu_baseline sample')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--debug-flags', type=int, default=None, help='sdb_set_debug_flags value (kernel variant experiments)')
     return ap.parse_args()
 
 
@@ -197,6 +198,8 @@ def run_b200(a):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
+    if a.debug_flags is not None:
+        _lib.load().sdb_set_debug_flags(a.debug_flags)
 
     T, C = a.days, a.cells_per_gpu
     idx = synth.daily_index(T)

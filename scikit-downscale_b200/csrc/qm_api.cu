@@ -55,7 +55,7 @@ static int pick_np(int max_len) {
     return -1;
 }
 
-static int g_debug_flags = 0;      // bit 0: force the generic kernels (testing)
+static int g_debug_flags = 0;      // bit 0: force the generic kernels (testing); bit 1: pipelined predict tile kernel
 
 }  // namespace sdb
 
@@ -137,8 +137,9 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
     cudaStream_t st = (cudaStream_t)stream;
     const int longest = max_len > max_fit_len ? max_len : max_fit_len;
     if (dtype == SDB_F32 && out_dtype == SDB_F32 && kind != KIND_SHIFT_TAB && longest <= 1024 && !(g_debug_flags & 1)) {
-        if (longest <= 256) return qm_predict_tile_np256(kind, p, st);
-        return qm_predict_tile_np1024(kind, p, st);
+        const bool pipelined = (g_debug_flags & 2) != 0;
+        if (longest <= 256) return qm_predict_tile_np256(kind, p, st, pipelined);
+        return qm_predict_tile_np1024(kind, p, st, pipelined);
     }
     switch (pick_np(max_len)) {
         case 256:   return qm_predict_np256(dtype, kind, p, st);

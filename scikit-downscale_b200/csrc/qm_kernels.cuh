@@ -335,8 +335,8 @@ static int launch_predict(const PredictParams& p, cudaStream_t st) {
 // fast tile kernels (qm_tile.cuh), float32 only, instantiated in qm_np256.cu / qm_np1024.cu
 int qm_fit_tile_np256(const FitParams& f, cudaStream_t st);
 int qm_fit_tile_np1024(const FitParams& f, cudaStream_t st);
-int qm_predict_tile_np256(int kind, const PredictParams& p, cudaStream_t st);
-int qm_predict_tile_np1024(int kind, const PredictParams& p, cudaStream_t st);
+int qm_predict_tile_np256(int kind, const PredictParams& p, cudaStream_t st, bool pipelined);
+int qm_predict_tile_np1024(int kind, const PredictParams& p, cudaStream_t st, bool pipelined);
 
 // per-size entry points, defined in qm_np<N>.cu
 #define SDB_DECLARE_SIZE(NP)                                                             \

@@ -37,12 +37,12 @@ template <int E>
 constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 2 * TileGeom<E>::NPS * 4; }
 
 // cooperative, coalesced load of one group's rows for the CTA's 8 cells into tile[cell][skew(j)].
-// cp.async (LDGSTS): every thread fires all its row segments back to back, no register staging,
-// one wait at the end — the whole tile costs one memory latency instead of one per batch.
+// cp.async (LDGSTS): every thread fires all its row segments back to back, no register staging;
+// the caller commits / waits, so a tile can be in flight while another one is being processed.
 template <int E>
-__device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
-                                          int64_t c0, const int32_t* __restrict__ rg, int n,
-                                          const uint8_t* __restrict__ valid) {
+__device__ __forceinline__ void issue_tile_load(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
+                                                int64_t c0, const int32_t* __restrict__ rg, int n,
+                                                const uint8_t* __restrict__ valid) {
     constexpr int NPS = TileGeom<E>::NPS;
     const int cc = threadIdx.x & (TILE_CT - 1);
     const int64_t c = c0 + cc;
@@ -59,7 +59,16 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
         for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT) dst[skew(j)] = 0.0f;
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+template <int PENDING>
+__device__ __forceinline__ void wait_tile_loads() { asm volatile("cp.async.wait_group %0;\n" :: "n"(PENDING) : "memory"); }
+
+template <int E>
+__device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
+                                          int64_t c0, const int32_t* __restrict__ rg, int n,
+                                          const uint8_t* __restrict__ valid) {
+    issue_tile_load<E>(tile, src, ld, C, c0, rg, n, valid);
+    wait_tile_loads<0>();
 }
 
 // ---------------------------------------------------------------- fit
@@ -210,17 +219,238 @@ static __device__ __noinline__ float mapped_value_general(const float* __restric
 }
 
 // ---------------------------------------------------------------- predict
+// One warp maps one (cell, group): the group's inputs are in the shared row myX, the outputs
+// (float bits) are left in the shared row R.  See the header comment of this file and DESIGN.md §4.
+template <int E, bool SHIFT>
+__device__ __forceinline__ void map_cell_group(const PredictParams& p, float* myX, uint32_t* R, int lane,
+                                               int64_t c, int n, int m, const int32_t* __restrict__ rg,
+                                               const float* __restrict__ S, double xc, double yc) {
+    using G = TileGeom<E>;
+    constexpr int LOG = G::LOG;
+    constexpr uint32_t QMAX = G::QMAX;
+    constexpr uint32_t IDX = (1u << LOG) - 1u;
+    const int j0 = lane * E;
+    const int j1 = (j0 + E < n) ? j0 + E : n;
+    const int rb = skew(j0);
+    const bool ratio = (p.mode == SDB_MODE_BCSD_P) && p.return_anoms;
+    const bool same = (n == m);
+
+    // final value of a member from its mapped value: restore the shift parked in R (float32)
+    // and remove the target climatology (bcsd.py:263,267 / 170-185)
+    auto finish = [&](int member, float val) {
+        double res;
+        if (SHIFT) {
+            res = (double)__uint_as_float(R[skew(member)]) + (double)val;
+            if (p.return_anoms) res = res - yc;
+        } else {
+            res = ratio ? (double)val / yc : (double)val;
+        }
+        R[skew(member)] = __float_as_uint((float)res);
+    };
+
+    // ---- 1. own members (+ 4 / 5 halo) to registers; key bounds from the plain value range
+    constexpr int HL = SHIFT ? 4 : 0, HR = SHIFT ? 5 : 0;
+    K32 v[E];
+    {
+        float xh[E + HL + HR];
+#pragma unroll
+        for (int i = 0; i < E + HL + HR; ++i) {
+            const int e = i - HL;                          // member offset inside / around the lane's block
+            const int jj = j0 + e;
+            // E == 32: the skew step only changes at the block edges → static offsets from the row base
+            const int addr = (E == 32) ? rb + e + (e < 0 ? -1 : (e >= 32 ? 1 : 0)) : skew(jj < 0 ? 0 : jj);
+            xh[i] = (jj >= 0 && jj < n) ? myX[addr] : 0.0f;
+        }
+        float lo32 = INFINITY, hi32 = -INFINITY;
+        bool bad = false;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (j0 + e < n) {
+                const float x = xh[e + HL];
+                lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x);
+                bad |= !isfinite(x);
+            }
+        }
+        if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
+        lo32 = warp_min(lo32); hi32 = warp_max(hi32);
+
+        // ---- 2. exact rank keys → monotone bucket number, packed with the member position.
+        // The bounds are a guess (value range + 1/8 margin); keys outside clamp to the end
+        // buckets, which keeps the map monotone — whatever shares a bucket is compared exactly.
+        if (SHIFT) {
+            const double range = (double)hi32 - (double)lo32;
+            const double lo = (double)lo32 - 0.125 * range, hi = (double)hi32 + 0.125 * range;
+            const double scale = (hi > lo && isfinite(hi - lo)) ? (double)(QMAX - 1) / (hi - lo) : 0.0;
+            double sum = 0.0;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) sum += (double)xh[i];
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int j = j0 + e;
+                if (j < n) {
+                    const double shift = div_count(sum, win_count(j, n)) - xc;
+                    const double t = (((double)xh[e + 4] - shift) - lo) * scale;
+                    uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
+                    q = q > QMAX - 1 ? QMAX - 1 : q;
+                    v[e].k = (q << LOG) | (uint32_t)j;
+                    R[rb + e] = __float_as_uint((float)shift);
+                } else {
+                    v[e].k = 0xffffffffu;
+                }
+                sum += (double)xh[e + 9];
+                sum -= (double)xh[e];
+            }
+        } else {
+            const float range = hi32 - lo32;
+            const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const int j = j0 + e;
+                if (j < n) {
+                    const float t = (xh[e] - lo32) * scale;
+                    uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
+                    q = q > QMAX - 1 ? QMAX - 1 : q;
+                    v[e].k = (q << LOG) | (uint32_t)j;
+                } else {
+                    v[e].k = 0xffffffffu;
+                }
+            }
+        }
+    }
+
+    // ---- 3. one 32-bit keys-only sort
+    sort_blocked<K32, E, 32>(v, lane, nullptr);
+    const uint32_t nxt_first = __shfl_down_sync(0xffffffffu, v[0].k, 1);
+    uint32_t bm_eq = 0;                       // bit e: sorted positions (pos, pos+1) share a bucket
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
+        bm_eq |= ((j0 + e + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG))) ? (1u << e) : 0u;
+    }
+    __syncwarp();                             // shifts parked in R are visible to every lane
+
+    // ---- 4. (member, rank) of every sorted position → mapped value → output
+    // mode 0: one member per bucket, rank = position + 1.
+    // mode 2: members sharing a bucket are compared exactly; runs of exact ties take the run end
+    //         (tie-max rank), an isolated inverted pair is swapped.
+    // mode 3: any other structure (3+ distinct keys in a bucket) → exact 64-bit sort of the group.
+    int mode = 0;
+    uint32_t bm_gt = 0, bm_tie = 0;           // bit e: pair (pos, pos+1) is inverted / exactly tied
+    uint32_t prev_gt = 0;                     // the pair (j0 - 1, j0) owned by the previous lane is inverted
+    int tie_carry = 0;                        // rank of a tie run that continues past this lane's last member
+    constexpr uint32_t EMASK = (E == 32) ? 0xffffffffu : ((1u << (E & 31)) - 1u);
+    if (__any_sync(0xffffffffu, bm_eq != 0)) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if ((bm_eq >> e) & 1u) {
+                const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
+                const int cmp = cmp_members<SHIFT>(myX, n, (int)(v[e].k & IDX), (int)(kn & IDX), xc);
+                bm_gt |= (cmp > 0) ? (1u << e) : 0u;
+                bm_tie |= (cmp == 0) ? (1u << e) : 0u;
+            }
+        }
+        // a non-tied same-bucket pair must be isolated: no other same-bucket pair touching it
+        const uint32_t nontie = bm_eq & ~bm_tie;
+        const uint32_t nxt_eq0 = __shfl_down_sync(0xffffffffu, bm_eq & 1u, 1);
+        const uint32_t prv_eqL = __shfl_up_sync(0xffffffffu, (bm_eq >> (E - 1)) & 1u, 1);
+        uint32_t touching = (bm_eq << 1) | (bm_eq >> 1);
+        if (lane > 0 && prv_eqL) touching |= 1u;
+        if (lane < 31 && nxt_eq0) touching |= 1u << (E - 1);
+        mode = __any_sync(0xffffffffu, (nontie & touching) != 0) ? 3 : 2;
+        prev_gt = __shfl_up_sync(0xffffffffu, (bm_gt >> (E - 1)) & 1u, 1);
+        if (lane == 0) prev_gt = 0;
+        // tie runs: a position's rank is 1 + the first position at/after it whose tie bit is clear
+        const uint32_t open = ~bm_tie & EMASK;
+        const int first_end = j0 + __ffs(open);
+        const uint32_t has = __ballot_sync(0xffffffffu, open != 0);
+        const uint32_t higher = (lane == 31) ? 0u : (has & ~((2u << lane) - 1u));
+        tie_carry = __shfl_sync(0xffffffffu, first_end, higher ? (__ffs(higher) - 1) : lane);
+    }
+
+    if (mode == 0 && same && !p.rank_out && (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0)) {
+        // the common case: one member per bucket, same length — the member at sorted position
+        // pos takes the fitted order statistic S[pos]; the lane's 32 values are 8 vector loads
+        float4 s4[E / 4];
+#pragma unroll
+        for (int q4 = 0; q4 < E / 4; ++q4) {
+            const int pos = j0 + 4 * q4;
+            if (pos + 3 < n) s4[q4] = __ldg(reinterpret_cast<const float4*>(S + pos));
+            else {
+                s4[q4].x = pos < n ? __ldg(S + pos) : 0.0f;
+                s4[q4].y = pos + 1 < n ? __ldg(S + pos + 1) : 0.0f;
+                s4[q4].z = pos + 2 < n ? __ldg(S + pos + 2) : 0.0f;
+                s4[q4].w = 0.0f;
+            }
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < E / 4; ++q4) {
+            const int pos = j0 + 4 * q4;
+            if (pos < n) finish((int)(v[4 * q4].k & IDX), s4[q4].x);
+            if (pos + 1 < n) finish((int)(v[4 * q4 + 1].k & IDX), s4[q4].y);
+            if (pos + 2 < n) finish((int)(v[4 * q4 + 2].k & IDX), s4[q4].z);
+            if (pos + 3 < n) finish((int)(v[4 * q4 + 3].k & IDX), s4[q4].w);
+        }
+    } else if (mode == 3) {
+        rank_exact64<E, SHIFT>(myX, n, xc, lane);            // ranks by member → input row
+        __syncwarp();
+        const uint32_t* Xu = reinterpret_cast<const uint32_t*>(myX);
+        for (int j = j0; j < j1; ++j) {
+            const int rk = (int)Xu[skew(j)];
+            if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
+            finish(j, same ? __ldg(S + rk - 1) : mapped_value_general(S, rk, n, m));
+        }
+    } else {
+        // every other case (ties / swapped pairs / T_pred != T_fit / rank instrumentation): the exact
+        // comparisons are done, the inputs are no longer needed — stage the sorted words over them
+        // and walk the lane's positions in a compact runtime loop (neighbours come from the row).
+        uint32_t* Xu = reinterpret_cast<uint32_t*>(myX);
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < E; ++e) Xu[rb + e] = v[e].k;
+        __syncwarp();
+        for (int e = 0; e < E; ++e) {
+            const int pos = j0 + e;
+            if (pos >= n) break;
+            int member = (int)(Xu[rb + e] & IDX);
+            int rk = pos + 1;
+            if (mode == 2) {
+                const uint32_t gt_here = (bm_gt >> e) & 1u;
+                const uint32_t gt_prev = (e == 0) ? prev_gt : (bm_gt >> (e - 1)) & 1u;
+                if (gt_here) member = (int)(Xu[skew(pos + 1)] & IDX);        // inverted pair: take the next member
+                else if (gt_prev) member = (int)(Xu[skew(pos - 1)] & IDX);   // ... and the next position takes this one
+                const uint32_t open = (~bm_tie & EMASK) >> e;                // exact ties: end of the run
+                rk = open ? (pos + __ffs(open)) : tie_carry;
+            }
+            if (p.rank_out) p.rank_out[(int64_t)rg[member] * p.ld_out + c] = rk;
+            finish(member, same ? __ldg(S + rk - 1) : mapped_value_general(S, rk, n, m));
+        }
+    }
+}
+
+// coalesced store of one output tile (rows of 8 cells)
+template <int E>
+__device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictParams& p, int64_t c0,
+                                           const int32_t* __restrict__ rg, int n) {
+    constexpr int NPS = TileGeom<E>::NPS;
+    const int cc = threadIdx.x & (TILE_CT - 1);
+    const int64_t cs = c0 + cc;
+    if (cs < p.C) {
+        float* outp = (float*)p.out + cs;
+        const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
+#pragma unroll 4
+        for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT)
+            __stcs(outp + (int64_t)rg[j] * p.ld_out, srcp[skew(j)]);
+    }
+}
+
+// grid = (cell tiles, groups): one (tile, group) per CTA
 template <int E, bool SHIFT>
 __global__ void __launch_bounds__(TILE_THREADS, 3)
 qm_predict_tile_kernel(const PredictParams p) {
-    using G = TileGeom<E>;
-    constexpr int NPS = G::NPS, LOG = G::LOG;
-    constexpr uint32_t QMAX = G::QMAX;
-    constexpr uint32_t IDX = (1u << LOG) - 1u;
+    constexpr int NPS = TileGeom<E>::NPS;
     extern __shared__ uint32_t smem_u[];
     float* tileX = reinterpret_cast<float*>(smem_u);                        // inputs of the group
     uint32_t* tileR = smem_u + TILE_CT * NPS;                               // shift → outputs (float bits)
-
     const int g = blockIdx.y;
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
     const int n = p.len[g];
@@ -242,233 +472,63 @@ qm_predict_tile_kernel(const PredictParams p) {
     }
     load_tile<E>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid);
     __syncthreads();
-
-    float* myX = tileX + warp * NPS;
     uint32_t* R = tileR + warp * NPS;
-    const int j0 = lane * E;
-    const int j1 = (j0 + E < n) ? j0 + E : n;
-    const int rb = skew(j0);
-
     if (in_range && !active) {
         for (int j = lane; j < n; j += 32) R[skew(j)] = __float_as_uint(NAN);
     } else if (active) {
-        const double xc = (double)xc_f, yc = (double)yc_f;
-        const bool ratio = (p.mode == SDB_MODE_BCSD_P) && p.return_anoms;
-        const bool same = (n == m);
-
-        // final value of a member from its mapped value: restore the shift parked in R (float32)
-        // and remove the target climatology (bcsd.py:263,267 / 170-185)
-        auto finish = [&](int member, float val) {
-            double res;
-            if (SHIFT) {
-                res = (double)__uint_as_float(R[skew(member)]) + (double)val;
-                if (p.return_anoms) res = res - yc;
-            } else {
-                res = ratio ? (double)val / yc : (double)val;
-            }
-            R[skew(member)] = __float_as_uint((float)res);
-        };
-
-        // ---- 1. own members (+ 4 / 5 halo) to registers; key bounds from the plain value range
-        constexpr int HL = SHIFT ? 4 : 0, HR = SHIFT ? 5 : 0;
-        K32 v[E];
-        {
-            float xh[E + HL + HR];
-#pragma unroll
-            for (int i = 0; i < E + HL + HR; ++i) {
-                const int e = i - HL;                          // member offset inside / around the lane's block
-                const int jj = j0 + e;
-                // E == 32: the skew step only changes at the block edges → static offsets from the row base
-                const int addr = (E == 32) ? rb + e + (e < 0 ? -1 : (e >= 32 ? 1 : 0)) : skew(jj < 0 ? 0 : jj);
-                xh[i] = (jj >= 0 && jj < n) ? myX[addr] : 0.0f;
-            }
-            float lo32 = INFINITY, hi32 = -INFINITY;
-            bool bad = false;
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if (j0 + e < n) {
-                    const float x = xh[e + HL];
-                    lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x);
-                    bad |= !isfinite(x);
-                }
-            }
-            if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
-            lo32 = warp_min(lo32); hi32 = warp_max(hi32);
-
-            // ---- 2. exact rank keys → monotone bucket number, packed with the member position.
-            // The bounds are a guess (value range + 1/8 margin); keys outside clamp to the end
-            // buckets, which keeps the map monotone — whatever shares a bucket is compared exactly.
-            if (SHIFT) {
-                const double range = (double)hi32 - (double)lo32;
-                const double lo = (double)lo32 - 0.125 * range, hi = (double)hi32 + 0.125 * range;
-                const double scale = (hi > lo && isfinite(hi - lo)) ? (double)(QMAX - 1) / (hi - lo) : 0.0;
-                double sum = 0.0;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) sum += (double)xh[i];
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int j = j0 + e;
-                    if (j < n) {
-                        const double shift = div_count(sum, win_count(j, n)) - xc;
-                        const double t = (((double)xh[e + 4] - shift) - lo) * scale;
-                        uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
-                        q = q > QMAX - 1 ? QMAX - 1 : q;
-                        v[e].k = (q << LOG) | (uint32_t)j;
-                        R[rb + e] = __float_as_uint((float)shift);
-                    } else {
-                        v[e].k = 0xffffffffu;
-                    }
-                    sum += (double)xh[e + 9];
-                    sum -= (double)xh[e];
-                }
-            } else {
-                const float range = hi32 - lo32;
-                const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int j = j0 + e;
-                    if (j < n) {
-                        const float t = (xh[e] - lo32) * scale;
-                        uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
-                        q = q > QMAX - 1 ? QMAX - 1 : q;
-                        v[e].k = (q << LOG) | (uint32_t)j;
-                    } else {
-                        v[e].k = 0xffffffffu;
-                    }
-                }
-            }
-        }
-
-        // ---- 3. one 32-bit keys-only sort
-        sort_blocked<K32, E, 32>(v, lane, nullptr);
-        const uint32_t nxt_first = __shfl_down_sync(0xffffffffu, v[0].k, 1);
-        uint32_t bm_eq = 0;                       // bit e: sorted positions (pos, pos+1) share a bucket
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-            bm_eq |= ((j0 + e + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG))) ? (1u << e) : 0u;
-        }
-        __syncwarp();                             // shifts parked in R are visible to every lane
-
-        // ---- 4. (member, rank) of every sorted position → mapped value → output
-        // mode 0: one member per bucket, rank = position + 1.
-        // mode 2: members sharing a bucket are compared exactly; runs of exact ties take the run end
-        //         (tie-max rank), an isolated inverted pair is swapped.
-        // mode 3: any other structure (3+ distinct keys in a bucket) → exact 64-bit sort of the group.
-        int mode = 0;
-        uint32_t bm_gt = 0, bm_tie = 0;           // bit e: pair (pos, pos+1) is inverted / exactly tied
-        uint32_t prev_gt = 0;                     // the pair (j0 - 1, j0) owned by the previous lane is inverted
-        int tie_carry = 0;                        // rank of a tie run that continues past this lane's last member
-        if (__any_sync(0xffffffffu, bm_eq != 0)) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                if ((bm_eq >> e) & 1u) {
-                    const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-                    const int cmp = cmp_members<SHIFT>(myX, n, (int)(v[e].k & IDX), (int)(kn & IDX), xc);
-                    bm_gt |= (cmp > 0) ? (1u << e) : 0u;
-                    bm_tie |= (cmp == 0) ? (1u << e) : 0u;
-                }
-            }
-            // a non-tied same-bucket pair must be isolated: no other same-bucket pair touching it
-            const uint32_t nontie = bm_eq & ~bm_tie;
-            const uint32_t nxt_eq0 = __shfl_down_sync(0xffffffffu, bm_eq & 1u, 1);
-            const uint32_t prv_eqL = __shfl_up_sync(0xffffffffu, (bm_eq >> (E - 1)) & 1u, 1);
-            uint32_t touching = (bm_eq << 1) | (bm_eq >> 1);
-            if (lane > 0 && prv_eqL) touching |= 1u;
-            if (lane < 31 && nxt_eq0) touching |= 1u << (E - 1);
-            mode = __any_sync(0xffffffffu, (nontie & touching) != 0) ? 3 : 2;
-            prev_gt = __shfl_up_sync(0xffffffffu, (bm_gt >> (E - 1)) & 1u, 1);
-            if (lane == 0) prev_gt = 0;
-            // tie runs: a position's rank is 1 + the first position at/after it whose tie bit is clear
-            const uint32_t emask = (E == 32) ? 0xffffffffu : ((1u << (E & 31)) - 1u);
-            const uint32_t open = ~bm_tie & emask;                 // bit e clear in bm_tie → run ends at pos
-            const int first_end = j0 + __ffs(open);               // 1-based rank of the first run end in this lane
-            const uint32_t has = __ballot_sync(0xffffffffu, open != 0);
-            const uint32_t higher = (lane == 31) ? 0u : (has & ~((2u << lane) - 1u));
-            tie_carry = __shfl_sync(0xffffffffu, first_end, higher ? (__ffs(higher) - 1) : lane);
-        }
-        // rank of sorted position j0 + e under the tie-max rule
-        auto tie_rank = [&](int e) -> int {
-            const uint32_t emask = (E == 32) ? 0xffffffffu : ((1u << (E & 31)) - 1u);
-            const uint32_t open = (~bm_tie & emask) >> e;
-            return open ? (j0 + e + __ffs(open)) : tie_carry;
-        };
-
-        if (mode == 0 && same && !p.rank_out && (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0)) {
-            // the common case: one member per bucket, same length — the member at sorted position
-            // pos takes the fitted order statistic S[pos]; the lane's 32 values are 8 vector loads
-            float4 s4[E / 4];
-#pragma unroll
-            for (int q4 = 0; q4 < E / 4; ++q4) {
-                const int pos = j0 + 4 * q4;
-                if (pos + 3 < n) s4[q4] = __ldg(reinterpret_cast<const float4*>(S + pos));
-                else {
-                    s4[q4].x = pos < n ? __ldg(S + pos) : 0.0f;
-                    s4[q4].y = pos + 1 < n ? __ldg(S + pos + 1) : 0.0f;
-                    s4[q4].z = pos + 2 < n ? __ldg(S + pos + 2) : 0.0f;
-                    s4[q4].w = 0.0f;
-                }
-            }
-#pragma unroll
-            for (int q4 = 0; q4 < E / 4; ++q4) {
-                const int pos = j0 + 4 * q4;
-                if (pos < n) finish((int)(v[4 * q4].k & IDX), s4[q4].x);
-                if (pos + 1 < n) finish((int)(v[4 * q4 + 1].k & IDX), s4[q4].y);
-                if (pos + 2 < n) finish((int)(v[4 * q4 + 2].k & IDX), s4[q4].z);
-                if (pos + 3 < n) finish((int)(v[4 * q4 + 3].k & IDX), s4[q4].w);
-            }
-        } else if (mode == 3) {
-            rank_exact64<E, SHIFT>(myX, n, xc, lane);            // ranks by member → input row
-            __syncwarp();
-            const uint32_t* Xu = reinterpret_cast<const uint32_t*>(myX);
-            for (int j = j0; j < j1; ++j) {
-                const int rk = (int)Xu[skew(j)];
-                if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
-                finish(j, same ? __ldg(S + rk - 1) : mapped_value_general(S, rk, n, m));
-            }
-        } else {
-            const uint32_t prv_last_k = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
-            {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int pos = j0 + e;
-                    if (pos < n) {
-                        int member = (int)(v[e].k & IDX);
-                        int rk = pos + 1;
-                        if (mode == 2) {
-                            const uint32_t gt_here = (bm_gt >> e) & 1u;
-                            const uint32_t gt_prev = (e == 0) ? prev_gt : (bm_gt >> (e == 0 ? 0 : e - 1)) & 1u;
-                            if (gt_here) {                       // inverted pair: this position takes the next member
-                                const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-                                member = (int)(kn & IDX);
-                            } else if (gt_prev) {                // ... and the next position takes this one
-                                const uint32_t kp = (e == 0) ? prv_last_k : v[e == 0 ? e : e - 1].k;
-                                member = (int)(kp & IDX);
-                            }
-                            rk = tie_rank(e);                    // exact ties: everyone takes the end of the run
-                        }
-                        if (p.rank_out) p.rank_out[(int64_t)rg[member] * p.ld_out + c] = rk;
-                        float val;
-                        if (same) val = __ldg(S + rk - 1);
-                        else      val = mapped_value_general(S, rk, n, m);
-                        finish(member, val);
-                    }
-                }
-            }
-        }
+        map_cell_group<E, SHIFT>(p, tileX + warp * NPS, R, lane, c, n, m, rg, S, (double)xc_f, (double)yc_f);
     }
     __syncthreads();
-    // ---- 5. coalesced store of the tile (rows of 8 cells)
-    {
-        const int cc = threadIdx.x & (TILE_CT - 1);
-        const int64_t cs = c0 + cc;
-        if (cs < p.C) {
-            float* outp = (float*)p.out + cs;
-            const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
-#pragma unroll 4
-            for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT)
-                __stcs(outp + (int64_t)rg[j] * p.ld_out, srcp[skew(j)]);
+    store_tile<E>(tileR, p, c0, rg, n);
+}
+
+// grid = (cell tiles): the CTA walks all groups of its 8 cells; the next group's tile is in flight
+// (cp.async, second input buffer) while the current one is sorted and mapped.
+template <int E, bool SHIFT>
+__global__ void __launch_bounds__(TILE_THREADS, 2)
+qm_predict_tile_pipe_kernel(const PredictParams p) {
+    constexpr int NPS = TileGeom<E>::NPS;
+    extern __shared__ uint32_t smem_u[];
+    float* tileX0 = reinterpret_cast<float*>(smem_u);
+    float* tileX1 = tileX0 + TILE_CT * NPS;
+    uint32_t* tileR = smem_u + 2 * TILE_CT * NPS;
+    const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = c0 + warp;
+    const bool in_range = c < p.C;
+    const bool active = in_range && (!p.valid || p.valid[c]);
+    const int G = p.n_groups;
+    const float* X = (const float*)p.X;
+    issue_tile_load<E>(tileX0, X, p.ld, p.C, c0, p.rows, p.len[0], p.valid);
+    for (int g = 0; g < G; ++g) {
+        float* cur = (g & 1) ? tileX1 : tileX0;
+        float* nxt = (g & 1) ? tileX0 : tileX1;
+        const int n = p.len[g];
+        const int32_t* rg = p.rows + (int64_t)g * p.max_len;
+        const int sg = p.state_gid[g];
+        const int m = p.fit_len[sg];
+        const float* S = (const float*)p.state + (active ? c : 0) * p.state_ld + p.state_off[sg];
+        float xc_f = 0.0f, yc_f = 0.0f;
+        if (active) {
+            if (SHIFT) xc_f = ((const float*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
+            if (p.mode != SDB_MODE_QM && p.return_anoms) yc_f = ((const float*)p.y_climo)[(int64_t)sg * p.ld_climo + c];
+            if (lane * 32 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(S + lane * 32));
         }
+        if (g + 1 < G) {
+            issue_tile_load<E>(nxt, X, p.ld, p.C, c0, p.rows + (int64_t)(g + 1) * p.max_len, p.len[g + 1], p.valid);
+            wait_tile_loads<1>();
+        } else {
+            wait_tile_loads<0>();
+        }
+        __syncthreads();                 // tile g has landed; the previous store has finished reading R
+        uint32_t* R = tileR + warp * NPS;
+        if (in_range && !active) {
+            for (int j = lane; j < n; j += 32) R[skew(j)] = __float_as_uint(NAN);
+        } else if (active) {
+            map_cell_group<E, SHIFT>(p, cur + warp * NPS, R, lane, c, n, m, rg, S, (double)xc_f, (double)yc_f);
+        }
+        __syncthreads();
+        store_tile<E>(tileR, p, c0, rg, n);
     }
 }
 
@@ -486,12 +546,20 @@ static int launch_fit_tile(const FitParams& f, cudaStream_t st) {
 }
 
 template <int E, bool SHIFT>
-static int launch_predict_tile(const PredictParams& p, cudaStream_t st) {
-    auto kern = qm_predict_tile_kernel<E, SHIFT>;
-    const size_t smem = predict_tile_smem<E>();
-    if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT), (unsigned)p.n_groups);
-    kern<<<grid, TILE_THREADS, smem, st>>>(p);
+static int launch_predict_tile(const PredictParams& p, cudaStream_t st, bool pipelined) {
+    if (pipelined) {
+        auto kern = qm_predict_tile_pipe_kernel<E, SHIFT>;
+        const size_t smem = (size_t)TILE_CT * 3 * TileGeom<E>::NPS * 4;
+        if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT));
+        kern<<<grid, TILE_THREADS, smem, st>>>(p);
+    } else {
+        auto kern = qm_predict_tile_kernel<E, SHIFT>;
+        const size_t smem = predict_tile_smem<E>();
+        if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT), (unsigned)p.n_groups);
+        kern<<<grid, TILE_THREADS, smem, st>>>(p);
+    }
     SDB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -39,14 +39,18 @@ def eng():
 
 
 class force_generic:
-    """Run the generic (any dtype / any length) kernels instead of the float32 tile kernels."""
+    """Kernel family selection for a block of code: 'tile' (default float32 tile kernels),
+    'generic' (any dtype / any length kernels), 'pipe' (tile kernels, software-pipelined predict).
+    ``True`` / ``False`` are accepted for generic / tile."""
+
+    FLAGS = {'tile': 0, 'generic': 1, 'pipe': 2, True: 1, False: 0}
 
     def __init__(self, on=True):
         self.on = on
 
     def __enter__(self):
         from skdownscale_b200 import _lib
-        self.old = _lib.load().sdb_set_debug_flags(1 if self.on else 0)
+        self.old = _lib.load().sdb_set_debug_flags(self.FLAGS[self.on])
 
     def __exit__(self, *a):
         from skdownscale_b200 import _lib
@@ -148,6 +152,12 @@ def _expected_rank_map(x, y):
 ])
 def test_bcsd_temperature_golden(dev, golden, name, kw):
     g = golden(name)
+    idx_f0 = synth.daily_index(len(g['Xtr']), str(g['start_fit']))
+    idx_p0 = synth.daily_index(len(g['Xp']), str(g['start_pred']))
+    with force_generic('pipe'):          # the software-pipelined predict kernel gives the same field
+        pw0 = pm().PointWiseDownscaler(pm().BcsdTemperature(**kw))
+        pw0.fit(g['Xtr'], g['ytr'], time=idx_f0)
+        assert_close(pw0.predict(g['Xp'], time=idx_p0), g['out'], scale=np.nanstd(g['ytr']))
     idx_f = synth.daily_index(len(g['Xtr']), str(g['start_fit']))
     idx_p = synth.daily_index(len(g['Xp']), str(g['start_pred']))
     pw = pm().PointWiseDownscaler(pm().BcsdTemperature(**kw))
@@ -203,7 +213,7 @@ def test_bcsd_errors(dev):
         pm().BcsdTemperature().fit(pd.DataFrame(np.zeros((10, 1)), index=idx[:10]), pd.DataFrame(np.zeros((10, 1)), index=idx[5:15]))
 
 
-@pytest.mark.parametrize('generic', [False, True])
+@pytest.mark.parametrize('generic', ['tile', 'generic', 'pipe'])
 @pytest.mark.parametrize('anoms', [True, False])
 def test_bcsd_temperature_vs_oracle_ranks(dev, anoms, generic):
     """30-year daily series, ragged cell count, NaN cells; ranks bit-exact, values 1e-5.
@@ -239,9 +249,15 @@ def _bcsd_temperature_vs_oracle_ranks(dev, anoms):
         assert yc[gi, 0] == oracle.bcsd._group_mean_like_pandas(ytr[rows, 0])
 
 
+@pytest.mark.parametrize('family', ['tile', 'pipe'])
 @pytest.mark.parametrize('case', ['outlier', 'clusters', 'constant', 'two_values'])
 @pytest.mark.parametrize('model', ['T', 'P'])
-def test_tile_kernel_bucket_fixups(dev, case, model):
+def test_tile_kernel_bucket_fixups(dev, case, model, family):
+    with force_generic(family):
+        _tile_kernel_bucket_fixups(dev, case, model)
+
+
+def _tile_kernel_bucket_fixups(dev, case, model):
     """Inputs built to defeat the 22-bit key quantisation of the tile kernels: a huge outlier
     squeezing every other value into one bucket (→ exact 64-bit fallback sort), clusters of
     near-duplicates one float32 ulp apart (→ local exact fix-up), constant series and
@@ -284,7 +300,7 @@ def test_tile_kernel_bucket_fixups(dev, case, model):
             assert_close(out[:, c], o.astype(np.float32), scale=np.std(ytr[:, c]))
 
 
-@pytest.mark.parametrize('generic', [False, True])
+@pytest.mark.parametrize('generic', ['tile', 'generic', 'pipe'])
 def test_bcsd_precipitation_vs_oracle(dev, generic):
     with force_generic(generic):
         _bcsd_precipitation_vs_oracle(dev)
