@@ -75,6 +75,12 @@ const char* sdb_last_error(void);
  * float32 tile kernels apply.  Returns the previous flags. */
 int sdb_set_debug_flags(int flags);
 
+/* Strided host<->device copy of a [height, width_bytes] block (cudaMemcpy2DAsync) on `stream`:
+ * how a column block (cell range) of a time-major host array travels to / from the device.
+ * kind: 0 = host to device, 1 = device to host.  Pitches in bytes. */
+int sdb_memcpy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                       int64_t width_bytes, int64_t height, int kind, void* stream);
+
 /* Largest group length supported by sdb_qm_fit / sdb_qm_predict. */
 int sdb_max_group_len(void);
 

@@ -24,6 +24,7 @@ SIGNATURES = {
     'sdb_last_error': (c_char_p, []),
     'sdb_max_group_len': (c_int, []),
     'sdb_set_debug_flags': (c_int, [c_int]),
+    'sdb_memcpy2d_async': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     'sdb_group_mean': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
                                c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'sdb_qm_fit': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -408,21 +408,47 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
 #pragma unroll
         for (int e = 0; e < E; ++e) Xu[rb + e] = v[e].k;
         __syncwarp();
+        // pass A: rank of every position (the row keeps the original member in the low bits, which is
+        // all a neighbour ever reads; the rank goes into the bits above)
         for (int e = 0; e < E; ++e) {
             const int pos = j0 + e;
             if (pos >= n) break;
-            int member = (int)(Xu[rb + e] & IDX);
             int rk = pos + 1;
             if (mode == 2) {
-                const uint32_t gt_here = (bm_gt >> e) & 1u;
-                const uint32_t gt_prev = (e == 0) ? prev_gt : (bm_gt >> (e - 1)) & 1u;
-                if (gt_here) member = (int)(Xu[skew(pos + 1)] & IDX);        // inverted pair: take the next member
-                else if (gt_prev) member = (int)(Xu[skew(pos - 1)] & IDX);   // ... and the next position takes this one
                 const uint32_t open = (~bm_tie & EMASK) >> e;                // exact ties: end of the run
                 rk = open ? (pos + __ffs(open)) : tie_carry;
             }
-            if (p.rank_out) p.rank_out[(int64_t)rg[member] * p.ld_out + c] = rk;
-            finish(member, same ? __ldg(S + rk - 1) : mapped_value_general(S, rk, n, m));
+            Xu[rb + e] = (Xu[rb + e] & IDX) | ((uint32_t)rk << LOG);
+        }
+        __syncwarp();
+        // pass B: four positions at a time — the fitted values are fetched together, then finished
+        for (int e0 = 0; e0 < E; e0 += 4) {
+            if (j0 + e0 >= n) break;
+            uint32_t member[4];
+            int rk[4];
+            float val[4];
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int e = e0 + d, pos = j0 + e;
+                const uint32_t w = Xu[rb + e];
+                member[d] = w & IDX;
+                rk[d] = (int)(w >> LOG);
+                if (mode == 2 && pos < n) {
+                    const uint32_t gt_here = (bm_gt >> e) & 1u;
+                    const uint32_t gt_prev = (e == 0) ? prev_gt : (bm_gt >> (e - 1)) & 1u;
+                    if (gt_here) member[d] = Xu[skew(pos + 1)] & IDX;        // inverted pair: take the next member
+                    else if (gt_prev) member[d] = Xu[skew(pos - 1)] & IDX;   // ... and the next position takes this one
+                }
+                val[d] = (same && pos < n) ? __ldg(S + rk[d] - 1) : 0.0f;
+            }
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int pos = j0 + e0 + d;
+                if (pos < n) {
+                    if (p.rank_out) p.rank_out[(int64_t)rg[member[d]] * p.ld_out + c] = rk[d];
+                    finish((int)member[d], same ? val[d] : mapped_value_general(S, rk[d], n, m));
+                }
+            }
         }
     }
 }

@@ -103,6 +103,16 @@ class QMFitted:
     nonfinite: torch.Tensor | None = None  # int32 [1]
     extra: dict = field(default_factory=dict)
 
+    def cells(self, c0: int, c1: int) -> 'QMFitted':
+        """View of the state of cells [c0, c1) (shares storage and the non-finite flag)."""
+        return QMFitted(dtype=self.dtype, n_cells=c1 - c0, sort_table=self.sort_table, state_off=self.state_off,
+                        state_ld=self.state_ld, sorted_state=self.sorted_state[c0:c1],
+                        fit_len_dev=self.fit_len_dev, state_off_dev=self.state_off_dev, mean_table=self.mean_table,
+                        x_climo=None if self.x_climo is None else self.x_climo[:, c0:c1],
+                        y_climo=None if self.y_climo is None else self.y_climo[:, c0:c1],
+                        valid=None if self.valid is None else self.valid[c0:c1], nonfinite=self.nonfinite,
+                        extra={})
+
     def check_finite(self):
         """Raise like the reference's sklearn validation (base.py:18-20) if a kernel met NaN/inf."""
         if self.nonfinite is not None and int(self.nonfinite.item()) != 0:
@@ -115,16 +125,77 @@ def cell_mask(first_row: torch.Tensor) -> torch.Tensor:
     return (~torch.isnan(first_row)).to(torch.uint8).contiguous()
 
 
-def group_mean(v: torch.Tensor, table: GroupTable, how: int, valid=None, nonfinite=None) -> torch.Tensor:
+def group_mean(v: torch.Tensor, table: GroupTable, how: int, valid=None, nonfinite=None, out=None) -> torch.Tensor:
     lib = _lib.load()
     ld = _check_2d(v, 'v')
     C = v.shape[1]
     rows, length = table.device(v.device)
-    out = torch.empty((table.n_groups, C), dtype=v.dtype, device=v.device)
+    if out is None:
+        out = torch.empty((table.n_groups, C), dtype=v.dtype, device=v.device)
+    ld_out = _check_2d(out, 'climo')
     _lib.check(lib.sdb_group_mean(_ptr(v), _code(v), ld, C, _ptr(rows), _ptr(length), table.n_groups,
-                                  table.rows.shape[1], how, _ptr(out), C, _ptr(valid), _ptr(nonfinite),
+                                  table.rows.shape[1], how, _ptr(out), ld_out, _ptr(valid), _ptr(nonfinite),
                                   _stream()), 'sdb_group_mean')
     return out
+
+
+def copy2d(dst: torch.Tensor, src: torch.Tensor, to_device: bool, stream=None) -> None:
+    """Asynchronous strided copy of a [rows, cols] block between host and device (both tensors may
+    be column slices of wider arrays) — cudaMemcpy2DAsync through the C ABI."""
+    lib = _lib.load()
+    if dst.shape != src.shape or dst.dim() != 2 or dst.dtype != src.dtype:
+        raise ValueError('copy2d needs two [rows, cols] tensors of the same shape and dtype')
+    if (dst.stride(1) != 1 and dst.shape[1] != 1) or (src.stride(1) != 1 and src.shape[1] != 1):
+        raise ValueError('copy2d needs unit stride along the columns')
+    es = dst.element_size()
+    rows, cols = dst.shape
+    dp = (dst.stride(0) if rows > 1 else cols) * es
+    sp = (src.stride(0) if rows > 1 else cols) * es
+    _lib.check(lib.sdb_memcpy2d_async(_ptr(dst), dp, _ptr(src), sp, cols * es, rows, 0 if to_device else 1,
+                                      stream if stream is not None else _stream()), 'sdb_memcpy2d_async')
+
+
+def alloc_state(dtype, n_cells: int, device, sort_table: GroupTable, mean_table: GroupTable | None = None,
+                need_x_climo: bool = False, need_y_climo: bool = True, with_valid: bool = False) -> QMFitted:
+    """Device storage of the fitted state of ``n_cells`` cells (filled by :func:`qm_fit_into`)."""
+    lib = _lib.load()
+    if sort_table.max_len > lib.sdb_max_group_len():
+        raise NotImplementedError(f'time groups longer than {lib.sdb_max_group_len()} steps are not supported yet '
+                                  f'(got {sort_table.max_len})')
+    lens = sort_table.len.astype(np.int64)
+    padded = (lens + 3) // 4 * 4                       # keep every group 16-byte aligned inside a record
+    off = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
+    state_ld = int(padded.sum())
+    mt = mean_table if mean_table is not None else sort_table
+    _, length = sort_table.device(device)
+    return QMFitted(dtype=dtype, n_cells=n_cells, sort_table=sort_table, state_off=off, state_ld=state_ld,
+                    sorted_state=torch.empty((n_cells, state_ld), dtype=dtype, device=device),
+                    fit_len_dev=length, state_off_dev=torch.from_numpy(off).to(device), mean_table=mt,
+                    x_climo=torch.empty((mt.n_groups, n_cells), dtype=dtype, device=device) if need_x_climo else None,
+                    y_climo=torch.empty((mt.n_groups, n_cells), dtype=dtype, device=device) if need_y_climo else None,
+                    valid=torch.ones(n_cells, dtype=torch.uint8, device=device) if with_valid else None,
+                    nonfinite=torch.zeros(1, dtype=torch.int32, device=device))
+
+
+def qm_fit_into(st: QMFitted, y: torch.Tensor, X: torch.Tensor | None = None,
+                mean_how: int = _lib.MEAN_GROUPBY) -> QMFitted:
+    """Run the fit kernels for the cells of ``st`` (a whole state or a :meth:`QMFitted.cells` view)."""
+    lib = _lib.load()
+    ld = _check_2d(y, 'y')
+    T, C = y.shape
+    if C != st.n_cells or y.dtype != st.dtype:
+        raise ValueError('y does not match the state block')
+    rows, length = st.sort_table.device(y.device)
+    _lib.check(lib.sdb_qm_fit(_ptr(y), _code(y), ld, C, _ptr(rows), _ptr(length), _ptr(st.state_off_dev),
+                              st.sort_table.n_groups, st.sort_table.rows.shape[1], _ptr(st.sorted_state),
+                              st.state_ld, _ptr(st.valid), _ptr(st.nonfinite), _stream()), 'sdb_qm_fit')
+    if st.y_climo is not None:
+        group_mean(y, st.mean_table, mean_how, st.valid, st.nonfinite, out=st.y_climo)
+    if st.x_climo is not None:
+        if X is None or X.shape != y.shape:
+            raise ValueError('X and y must have the same shape')
+        group_mean(X, st.mean_table, mean_how, st.valid, st.nonfinite, out=st.x_climo)
+    return st
 
 
 def qm_fit(y: torch.Tensor, sort_table: GroupTable, *, valid=None, X=None, mean_table=None,
@@ -133,36 +204,11 @@ def qm_fit(y: torch.Tensor, sort_table: GroupTable, *, valid=None, X=None, mean_
 
     BcsdTemperature.fit / BcsdPrecipitation.fit / QuantileMapper.fit for all cells
     (bcsd.py:115-147, 197-228; quantile.py:81-107)."""
-    lib = _lib.load()
-    ld = _check_2d(y, 'y')
-    T, C = y.shape
-    if sort_table.max_len > lib.sdb_max_group_len():
-        raise NotImplementedError(f'time groups longer than {lib.sdb_max_group_len()} steps are not supported yet '
-                                  f'(got {sort_table.max_len})')
-    lens = sort_table.len.astype(np.int64)
-    padded = (lens + 3) // 4 * 4                       # keep every group 16-byte aligned inside a record
-    off = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
-    state_ld = int(padded.sum())
-    dev = y.device
-    state = torch.empty((C, state_ld), dtype=y.dtype, device=dev)
-    off_dev = torch.from_numpy(off).to(dev)
-    rows, length = sort_table.device(dev)
-    nonfinite = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(lib.sdb_qm_fit(_ptr(y), _code(y), ld, C, _ptr(rows), _ptr(length), _ptr(off_dev),
-                              sort_table.n_groups, sort_table.rows.shape[1], _ptr(state), state_ld,
-                              _ptr(valid), _ptr(nonfinite), _stream()), 'sdb_qm_fit')
-    st = QMFitted(dtype=y.dtype, n_cells=C, sort_table=sort_table, state_off=off, state_ld=state_ld,
-                  sorted_state=state, fit_len_dev=length, state_off_dev=off_dev, valid=valid,
-                  nonfinite=nonfinite)
-    mt = mean_table if mean_table is not None else sort_table
-    st.mean_table = mt
-    if want_y_climo:
-        st.y_climo = group_mean(y, mt, mean_how, valid, nonfinite)
-    if X is not None:
-        if X.shape != y.shape:
-            raise ValueError(f'X {tuple(X.shape)} and y {tuple(y.shape)} must have the same shape')
-        st.x_climo = group_mean(X, mt, mean_how, valid, nonfinite)
-    return st
+    _check_2d(y, 'y')
+    st = alloc_state(y.dtype, y.shape[1], y.device, sort_table, mean_table, need_x_climo=X is not None,
+                     need_y_climo=want_y_climo)
+    st.valid = valid
+    return qm_fit_into(st, y, X, mean_how)
 
 
 def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, return_anoms: bool = False,
@@ -195,6 +241,10 @@ def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, r
             st.extra[key] = (None if x_climo is None else x_climo.index_select(0, sel).contiguous(),
                              None if y_climo is None else y_climo.index_select(0, sel).contiguous())
         x_climo, y_climo = st.extra[key]
+    ld_climo = C
+    for cl in (x_climo, y_climo):
+        if cl is not None:
+            ld_climo = _check_2d(cl, 'climo')
     gid_dev = torch.from_numpy(gid).to(dev)
     rows, length = table.device(dev)
     od = out_dtype or X.dtype
@@ -211,7 +261,7 @@ def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, r
                                   _ptr(rows), _ptr(length), _ptr(gid_dev), table.n_groups, table.rows.shape[1],
                                   _ptr(st.fit_len_dev), _ptr(st.state_off_dev), st.sort_table.max_len,
                                   _ptr(st.sorted_state), st.state_ld,
-                                  _ptr(x_climo), _ptr(y_climo), C,
+                                  _ptr(x_climo), _ptr(y_climo), ld_climo,
                                   int(bool(return_anoms)), _ptr(nbr_dev),
                                   _ptr(out), _TORCH_CODE[out.dtype], ld_out, _ptr(rank),
                                   _ptr(st.valid), _ptr(st.nonfinite), _stream()), 'sdb_qm_predict')

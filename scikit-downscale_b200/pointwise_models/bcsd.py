@@ -107,6 +107,114 @@ class BcsdBase(TimeSynchronousDownscaler):
         return engine.qm_predict(self._state, X, table, self._mode, return_anoms=self.return_anoms,
                                  roll_nbr=nbr, out_dtype=out_dtype, want_rank=want_rank, out=out)
 
+    # ------------------------------------------------------------------ host arrays: chunked H2D → kernels → D2H
+    @staticmethod
+    def _host2d(a, name):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
+        if t.is_cuda or t.dim() != 2:
+            raise ValueError(f'{name} must be a host [time, cell] array')
+        if t.shape[1] > 1 and t.stride(1) != 1:
+            t = t.contiguous()
+        return t
+
+    @staticmethod
+    def _spans(n_cells, chunk):
+        return [(c0, min(c0 + chunk, n_cells)) for c0 in range(0, n_cells, chunk)]
+
+    def fit_host(self, X, y, index, device=None, chunk_cells: int = 16384):
+        """fit from HOST arrays ``[T, C]``: cell chunks travel host → device on a copy stream
+        (strided 2-D DMA, pinned memory recommended) while the previous chunk is being fitted;
+        the fitted state of all cells stays on the device."""
+        dev = cuda_device(device)
+        Xh, yh = self._host2d(X, 'X'), self._host2d(y, 'y')
+        if Xh.shape != yh.shape:
+            raise ValueError(f'X {tuple(Xh.shape)} and y {tuple(yh.shape)} must have the same shape')
+        if Xh.dtype != yh.dtype or yh.dtype not in (torch.float32, torch.float64):
+            Xh, yh = Xh.to(torch.float64), yh.to(torch.float64)
+        T, C = yh.shape
+        self._pre_fit()
+        sort_t, mean_t, how = self._fit_tables(index)
+        st = engine.alloc_state(yh.dtype, C, dev, sort_t, mean_t, need_x_climo=self._needs_x_climo,
+                                need_y_climo=True, with_valid=True)
+        chunk = max(8, min(chunk_cells, C))
+        with torch.cuda.device(dev):
+            comp = torch.cuda.current_stream(dev)
+            s_in = torch.cuda.Stream(dev)
+            buf_y = [torch.empty((T, chunk), dtype=yh.dtype, device=dev) for _ in range(2)]
+            buf_x = [torch.empty((T if self._needs_x_climo else 1, chunk), dtype=yh.dtype, device=dev) for _ in range(2)]
+            free = [None, None]
+            for k, (c0, c1) in enumerate(self._spans(C, chunk)):
+                b, w = k & 1, c1 - c0
+                if free[b] is not None:
+                    s_in.wait_event(free[b])
+                engine.copy2d(buf_y[b][:, :w], yh[:, c0:c1], True, stream=s_in.cuda_stream)
+                xrows = T if self._needs_x_climo else 1          # precipitation only needs X for the cell mask
+                engine.copy2d(buf_x[b][:xrows, :w], Xh[:xrows, c0:c1], True, stream=s_in.cuda_stream)
+                landed = torch.cuda.Event()
+                landed.record(s_in)
+                comp.wait_event(landed)
+                view = st.cells(c0, c1)
+                view.valid.copy_(engine.cell_mask(buf_x[b][0, :w]))          # core.py:35-37
+                engine.qm_fit_into(view, buf_y[b][:, :w], buf_x[b][:, :w] if self._needs_x_climo else None, how)
+                free[b] = torch.cuda.Event()
+                free[b].record(comp)
+        self._state = st
+        self.n_features_in_ = 1
+        return self
+
+    def predict_host(self, X, index, out=None, device=None, chunk_cells: int = 16384):
+        """predict from a HOST array ``[T, C]`` into a host array (``out`` or a new pinned tensor):
+        H2D of chunk k+1, the kernels of chunk k and D2H of chunk k-1 overlap on three streams."""
+        if not hasattr(self, '_state'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
+                                 "appropriate arguments before using this estimator.")
+        if self.timestep == 'daily' and self.return_anoms:
+            raise ValueError('shape of climo is not equal to input array')
+        st = self._state
+        dev = st.sorted_state.device
+        Xh = self._host2d(X, 'X')
+        if Xh.dtype != st.dtype:
+            Xh = Xh.to(st.dtype)
+        T, C = Xh.shape
+        if C != st.n_cells:
+            raise ValueError(f'X has {C} cells, the model was fitted on {st.n_cells}')
+        if out is None:
+            out_h = torch.empty((T, C), dtype=st.dtype, pin_memory=True)
+        else:
+            out_h = self._host2d(out, 'out')
+            if out_h.shape != (T, C) or out_h.dtype != st.dtype:
+                raise ValueError('out must be a host array shaped and typed like the result')
+        table, nbr = self._predict_tables(index)
+        chunk = max(8, min(chunk_cells, C))
+        with torch.cuda.device(dev):
+            comp = torch.cuda.current_stream(dev)
+            s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            buf_x = [torch.empty((T, chunk), dtype=st.dtype, device=dev) for _ in range(2)]
+            buf_o = [torch.empty((T, chunk), dtype=st.dtype, device=dev) for _ in range(2)]
+            x_free, o_free = [None, None], [None, None]
+            for k, (c0, c1) in enumerate(self._spans(C, chunk)):
+                b, w = k & 1, c1 - c0
+                if x_free[b] is not None:
+                    s_in.wait_event(x_free[b])
+                engine.copy2d(buf_x[b][:, :w], Xh[:, c0:c1], True, stream=s_in.cuda_stream)
+                landed = torch.cuda.Event()
+                landed.record(s_in)
+                comp.wait_event(landed)
+                if o_free[b] is not None:
+                    comp.wait_event(o_free[b])
+                engine.qm_predict(st.cells(c0, c1), buf_x[b][:, :w], table, self._mode,
+                                  return_anoms=self.return_anoms, roll_nbr=nbr, out=buf_o[b][:, :w])
+                done = torch.cuda.Event()
+                done.record(comp)
+                x_free[b] = done
+                s_out.wait_event(done)
+                engine.copy2d(out_h[:, c0:c1], buf_o[b][:, :w], False, stream=s_out.cuda_stream)
+                o_free[b] = torch.cuda.Event()
+                o_free[b].record(s_out)
+            s_out.synchronize()
+        st.check_finite()
+        return out_h
+
     # ------------------------------------------------------------------ per-cell API of the reference
     def fit(self, X, y):
         X, y = self._frames(X, y)

@@ -58,11 +58,14 @@ class PointWiseDownscaler:
     device : torch device, optional (default: current CUDA device)
     """
 
-    def __init__(self, model, dim: str = 'time', device=None) -> None:
+    def __init__(self, model, dim: str = 'time', device=None, chunk_cells: int = 16384) -> None:
         self._dim = dim
         self._model = model
         self._models = None
         self._device = device
+        # host blocks with more cells than this are streamed through the GPU in cell chunks
+        # (H2D / kernels / D2H overlapped) instead of being copied whole
+        self._chunk_cells = chunk_cells
         if not hasattr(model, 'fit'):
             raise TypeError(f'Type {type(model)} does not have the fit method required by PointWiseDownscaler')
 
@@ -136,10 +139,21 @@ class PointWiseDownscaler:
             raise TypeError(f'unsupported fit parameters on the B200 path: {sorted(kws)}')
         dev = self._dev()
         bx = self._to_block(X, fd, time)
+        model = self._model
+        if self._streamed(bx) and args:
+            by = self._to_block_y(args[0], fd, time)
+            if bx.index is None:
+                raise ValueError('BCSD models need the time axis labels: pass time=<DatetimeIndex>')
+            if bx.data.shape[1] != 1:
+                raise ValueError(f'BCSD only supports 1 feature, found {bx.data.shape[1]}')
+            model.fit_host(bx.data[:, 0], by.data[:, 0], bx.index, device=dev, chunk_cells=self._chunk_cells)
+            model.check_fit()
+            self._models = model
+            self._valid = model._state.valid
+            return
         x = engine.as_device(bx.data, dev)
         x = self._float(x)
         valid = engine.cell_mask(x[0, 0])                      # core.py:35-37,77-78
-        model = self._model
         if isinstance(model, QuantileMapper):
             if x.shape[1] != 1:
                 raise ValueError('CunnaneTransformer.fit() only supports a single feature')
@@ -167,6 +181,15 @@ class PointWiseDownscaler:
         model.check_fit() if hasattr(model, 'check_fit') else None
         self._models = model
         self._valid = valid
+
+    def _streamed(self, blk) -> bool:
+        """Host-resident BCSD block big enough to be worth the chunked copy/compute pipeline."""
+        if not isinstance(self._model, BcsdBase) or blk.kind == 'xarray':
+            return False
+        d = blk.data
+        on_host = (not isinstance(d, torch.Tensor)) or (not d.is_cuda)
+        ok_dtype = (d.dtype in (torch.float32, torch.float64)) if isinstance(d, torch.Tensor) else (d.dtype in (np.float32, np.float64))
+        return on_host and ok_dtype and d.shape[-1] > self._chunk_cells
 
     def _to_block_y(self, y, fd, time):
         multi = self._multi_feature()
@@ -203,13 +226,21 @@ class PointWiseDownscaler:
         time = kws.pop('time', None)
         fd = kws.pop('feature_dim')
         kws.pop('along_dim', None)
+        kws_out = kws.pop('out', None)      # optional (pinned) host array [time, cells] receiving a streamed result
         if kws:
             raise TypeError(f'unsupported predict parameters on the B200 path: {sorted(kws)}')
         model = self._models
         if isinstance(model, QuantileMapper):
             raise AttributeError("'QuantileMapper' object has no attribute 'predict'")
         dev = self._dev()
+        out_host = kws_out
         bx = self._to_block(X, fd, time)
+        if self._streamed(bx):
+            if bx.index is None:
+                raise ValueError('BCSD models need the time axis labels: pass time=<DatetimeIndex>')
+            res = model.predict_host(bx.data[:, 0], bx.index, out=out_host, chunk_cells=self._chunk_cells)
+            res = res.reshape((res.shape[0],) + tuple(bx.cell_shape))
+            return res if bx.kind == 'torch' else res.numpy()
         x = self._float(engine.as_device(bx.data, dev))
         if isinstance(model, BcsdBase):
             if bx.index is None:

@@ -429,3 +429,39 @@ def test_analog_masked_cells_and_small_train(dev):
     assert np.isnan(got[:, :, 2]).all()
     ref = oracle.pointwise_fit_predict({'name': 'PureAnalog', 'n_analogs': 10, 'kind': 'mean_analogs'}, Xtr, ytr, Xq)
     assert_close(got, ref, scale=1.0)
+
+
+# ------------------------------------------------------------------ streamed host pipeline
+@pytest.mark.parametrize('model_name', ['T', 'P'])
+def test_streamed_host_pipeline_matches_whole_block(dev, model_name):
+    """host arrays streamed through the GPU in cell chunks (copy / compute / copy-back overlapped)
+    give exactly the field of the whole-block path; ragged last chunk, NaN cells, pinned `out`."""
+    T, C = 1461, 77
+    idx = synth.daily_index(T)
+    if model_name == 'T':
+        Xtr, ytr, Xp = synth.temperature(T, C, seed=31)
+        mk = lambda: pm().BcsdTemperature()          # noqa: E731
+    else:
+        Xtr, ytr, Xp = synth.precipitation(T, C, seed=32)
+        mk = lambda: pm().BcsdPrecipitation()        # noqa: E731
+    for c in (3, 40, 76):
+        Xtr[:, c] = np.nan
+    whole = pm().PointWiseDownscaler(mk(), chunk_cells=1 << 30)
+    whole.fit(Xtr, ytr, time=idx)
+    ref = whole.predict(Xp, time=idx)
+    streamed = pm().PointWiseDownscaler(mk(), chunk_cells=16)
+    streamed.fit(Xtr, ytr, time=idx)
+    got = streamed.predict(Xp, time=idx)
+    assert isinstance(got, np.ndarray) and got.dtype == Xp.dtype and got.shape == ref.shape
+    np.testing.assert_array_equal(got, ref)
+    # torch host tensors + caller-provided pinned output buffer, 3-D cell shape
+    out = torch.empty((T, C), dtype=torch.float32, pin_memory=True)
+    streamed.fit(torch.from_numpy(Xtr).pin_memory(), torch.from_numpy(ytr).pin_memory(), time=idx)
+    got2 = streamed.predict(torch.from_numpy(Xp).pin_memory(), time=idx, out=out)
+    assert isinstance(got2, torch.Tensor) and got2.data_ptr() == out.data_ptr()
+    np.testing.assert_array_equal(got2.numpy(), ref)
+    # a NaN inside an unmasked cell is still an error (base.py:18-20)
+    bad = ytr.copy()
+    bad[7, 50] = np.nan
+    with pytest.raises(ValueError, match='NaN'):
+        streamed.fit(Xtr, bad, time=idx)
