@@ -47,7 +47,7 @@ def parse():
     ap.add_argument('--cells-per-gpu', type=int, default=CELLS_PER_GPU)
     ap.add_argument('--days', type=int, default=DAYS)
     ap.add_argument('--e2e-steps', type=int, default=2)
-    ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target CPU time of the cpu_baseline sample')
+    ap.add_argument('--cpu-seconds', type=float, default=10.0, help='target CPU time of the cpu_baseline sample')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--debug-flags', type=int, default=None, help='sdb_set_debug_flags value (kernel variant experiments)')
@@ -67,27 +67,47 @@ def _oracle_cells(args):
     return time.perf_counter() - t0
 
 
+_POOL = {}
+
+
+def _pool(cores: int):
+    """One persistent joblib/loky pool per run, warmed up (worker start-up and imports are not part
+    of the measured sample)."""
+    from joblib import Parallel, delayed
+    if cores not in _POOL:
+        par = Parallel(n_jobs=cores)
+        par(delayed(_oracle_cells)((365, i, 1, 7)) for i in range(cores))
+        _POOL[cores] = par
+    return _POOL[cores]
+
+
 def cpu_sample(T: int, n_cells: int, cores: int):
     """Time the oracle port on ``n_cells`` cells spread over ``cores`` worker processes."""
-    from joblib import Parallel, delayed
+    from joblib import delayed
+    par = _pool(cores)
     per = max(1, n_cells // cores)
     jobs = [(T, i * per, per, 1000) for i in range(cores)]
     t0 = time.perf_counter()
-    Parallel(n_jobs=cores)(delayed(_oracle_cells)(j) for j in jobs)
+    par(delayed(_oracle_cells)(j) for j in jobs)
     wall = time.perf_counter() - t0
     done = per * cores
     return done * T / wall, done, wall
 
 
+def cpu_cells(T: int, cores: int, target_seconds: float) -> int:
+    _oracle_cells((T, 0, 1, 1))                         # import + warm-up in this process
+    t1 = _oracle_cells((T, 0, 2, 1)) / 2                # seconds per cell per core
+    per_worker = int(max(1, min(400, target_seconds / max(t1, 1e-4))))
+    return per_worker * cores
+
+
 def cpu_baseline(T: int, target_seconds: float):
     cores = os.cpu_count() or 1
-    _oracle_cells((T, 0, 1, 1))                         # import + warm-up
-    t1 = _oracle_cells((T, 0, 2, 1)) / 2                # seconds per cell per core
-    n_cells = int(max(cores, min(4096, cores * target_seconds / max(t1, 1e-4))))
+    n_cells = cpu_cells(T, cores, target_seconds)
     value, done, wall = cpu_sample(T, n_cells, cores)
     return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'sample': f'oracle (numpy port of the reference algorithm) BcsdTemperature fit+predict on {done} cells x {T} days, '
-                      f'{cores} joblib processes, {wall:.1f} s wall'}
+                      f'{cores} joblib worker processes (pool warmed up), {wall:.1f} s wall'}
 
 
 def run_reference(a):
@@ -97,10 +117,8 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    _oracle_cells((a.days, 0, 1, 1))
-    t1 = _oracle_cells((a.days, 0, 2, 1)) / 2
     budget = 120.0 / max(1, a.steps + a.warmup)        # keep the whole run within a few minutes
-    n_cells = int(max(cores, min(2048, cores * min(budget, 20.0) / max(t1, 1e-4))))
+    n_cells = cpu_cells(a.days, cores, min(budget, 15.0))
     for _ in range(a.warmup):
         cpu_sample(a.days, n_cells, cores)
     vals, walls, done = [], [], 0

@@ -9,7 +9,10 @@
 // The k-nearest-neighbour search is an EXACT float64 brute force: squared Euclidean
 // distance accumulated feature by feature with separate multiply and add (-fmad=false),
 // which reproduces sklearn KDTree's neighbour indices bit for bit on tie-free data
-// (lowest train index first on exact ties).  One thread owns one query timestep and keeps
+// (lowest train index first on exact ties).  For float32 inputs a float32 distance (FMA,
+// one 16-byte shared-memory read per training point) screens the candidates first: its
+// relative error (< 1e-6) is covered by the slack of the bound, so every point whose exact
+// distance could enter the list is still evaluated exactly — results are unchanged.  One thread owns one query timestep and keeps
 // its running top-k; the CTA streams the cell's training window through shared memory
 // (float64, broadcast reads).  The work is FP64-pipe bound — there is no GEMM here (K = p
 // is 1..8 and the `|a|^2 - 2ab + |b|^2` trick would break index exactness), so no tensor
@@ -25,7 +28,8 @@
 namespace sdb {
 
 constexpr int AN_THREADS = 256;     // queries per CTA
-template <int P> struct AnChunk { static constexpr int value = (P <= 4) ? 1024 : 512; };   // training points staged per pass (<= 32 KB of float64)
+template <int P> struct AnChunk { static constexpr int value = (P <= 3) ? 1024 : (P == 4 ? 768 : 384); };   // training points staged per pass
+template <int P> struct AnFStride { static constexpr int value = (P <= 4) ? 4 : 8; };                   // float32 copy: 16-byte rows
 constexpr int AN_KREG = 16;         // top-k list kept in registers up to this k
 constexpr int AN_PMAX = 8;          // generic-feature kernel handles up to this many predictors
 
@@ -182,7 +186,10 @@ template <typename T, int P, int KREG>
 __global__ void __launch_bounds__(AN_THREADS)
 analog_kernel(const AnalogParams a) {
     constexpr int AN_CHUNK = AnChunk<P>::value;
+    constexpr int PF = AnFStride<P>::value;
+    constexpr bool FILTER = (sizeof(T) == 4);         // float32 inputs: cheap float32 distance bound first
     __shared__ double chunk[AN_CHUNK * P];
+    __shared__ __align__(16) float chunkf[FILTER ? AN_CHUNK * PF : 4];
     const int n_tiles = (a.t_query + AN_THREADS - 1) / AN_THREADS;
     const int64_t c = blockIdx.x / n_tiles;           // consecutive CTAs share a cell: its window stays in L2
     const int tile = blockIdx.x - (int)(c * n_tiles);
@@ -198,9 +205,13 @@ analog_kernel(const AnalogParams a) {
     const int q = tile * AN_THREADS + threadIdx.x;
     const bool live = q < a.t_query;
     double xq[P];
+    float xqf[PF];
+#pragma unroll
+    for (int f = 0; f < PF; ++f) xqf[f] = 0.0f;
 #pragma unroll
     for (int f = 0; f < P; ++f) {
         xq[f] = (live && f < p) ? (double)Xq[((int64_t)q * a.p + f) * a.ld + c] : 0.0;
+        xqf[f] = (float)xq[f];
         if (live && f < p && a.nonfinite && !isfinite(xq[f])) atomicOr(a.nonfinite, 1);
     }
     // running top-k, ascending by (distance, index)
@@ -211,19 +222,46 @@ analog_kernel(const AnalogParams a) {
     for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) { bd[i] = INFINITY; bi[i] = -1; }
     if (KREG == 0) for (int i = 0; i < k; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
     double worst = INFINITY;                          // current k-th best distance
+    float worstf = INFINITY;                          // float32 upper bound of it (relative slack 1e-6 >> float32 error)
 
     for (int t0 = 0; t0 < a.t_fit; t0 += AN_CHUNK) {
         const int nt = min(AN_CHUNK, a.t_fit - t0);
         __syncthreads();
         for (int i = threadIdx.x; i < nt * p; i += AN_THREADS) {
             const int t = i / p, f = i - t * p;
-            const double xv = (double)Xtr[((int64_t)(t0 + t) * a.p + f) * a.ld + c];
+            const T raw = Xtr[((int64_t)(t0 + t) * a.p + f) * a.ld + c];
+            const double xv = (double)raw;
             if (a.nonfinite && tile == 0 && !isfinite(xv)) atomicOr(a.nonfinite, 1);
             chunk[t * P + f] = xv;
+            if (FILTER) chunkf[t * PF + f] = (float)raw;
+        }
+        if (FILTER && PF > P) {
+            for (int i = threadIdx.x; i < nt * (PF - P); i += AN_THREADS) {
+                const int t = i / (PF - P), f = P + (i - t * (PF - P));
+                chunkf[t * PF + f] = 0.0f;
+            }
+        }
+        if (FILTER && P == AN_PMAX && p < P) {
+            for (int i = threadIdx.x; i < nt * (P - p); i += AN_THREADS) {
+                const int t = i / (P - p), f = p + (i - t * (P - p));
+                chunkf[t * PF + f] = 0.0f;
+            }
         }
         __syncthreads();
         if (!live) continue;
         for (int t = 0; t < nt; ++t) {
+            if (FILTER) {
+                // float32 lower-bound test: the exact float64 distance is only evaluated for the few
+                // points that could enter the list (d32 <= worst * (1 + 1e-6) whenever d64 < worst)
+                float d32 = 0.0f;
+#pragma unroll
+                for (int f4 = 0; f4 < PF; f4 += 4) {
+                    const float4 cf = *reinterpret_cast<const float4*>(&chunkf[t * PF + f4]);
+                    const float d0 = xqf[f4] - cf.x, d1 = xqf[f4 + 1] - cf.y, d2 = xqf[f4 + 2] - cf.z, d3 = xqf[f4 + 3] - cf.w;
+                    d32 = fmaf(d0, d0, d32); d32 = fmaf(d1, d1, d32); d32 = fmaf(d2, d2, d32); d32 = fmaf(d3, d3, d32);
+                }
+                if (!(d32 <= worstf)) continue;
+            }
             double d = 0.0;
 #pragma unroll
             for (int f = 0; f < P; ++f) {
@@ -265,6 +303,7 @@ analog_kernel(const AnalogParams a) {
                     bd[pos] = d; bi[pos] = id;
                     worst = bd[0];
                 }
+                worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
             }
         }
     }
