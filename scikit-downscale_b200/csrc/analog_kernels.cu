@@ -28,7 +28,8 @@
 namespace sdb {
 
 constexpr int AN_THREADS = 256;     // queries per CTA
-template <int P> struct AnChunk { static constexpr int value = (P <= 3) ? 1024 : (P == 4 ? 768 : 384); };   // training points staged per pass
+template <int P> struct AnChunk { static constexpr int value = (P <= 3) ? 512 : (P == 4 ? 384 : 192); };    // training points staged per pass
+constexpr int AN_QD = 8;            // per-lane queue of accepted candidates (register-list kernels)
 template <int P> struct AnFStride { static constexpr int value = (P <= 4) ? 4 : 8; };                   // float32 copy: 16-byte rows
 constexpr int AN_KREG = 16;         // top-k list kept in registers up to this k
 constexpr int AN_PMAX = 8;          // generic-feature kernel handles up to this many predictors
@@ -190,6 +191,8 @@ analog_kernel(const AnalogParams a) {
     constexpr bool FILTER = (sizeof(T) == 4);         // float32 inputs: cheap float32 distance bound first
     __shared__ double chunk[AN_CHUNK * P];
     __shared__ __align__(16) float chunkf[FILTER ? AN_CHUNK * PF : 4];
+    __shared__ double qd[(KREG > 0) ? AN_QD * AN_THREADS : 1];
+    __shared__ int qi[(KREG > 0) ? AN_QD * AN_THREADS : 1];
     const int n_tiles = (a.t_query + AN_THREADS - 1) / AN_THREADS;
     const int64_t c = blockIdx.x / n_tiles;           // consecutive CTAs share a cell: its window stays in L2
     const int tile = blockIdx.x - (int)(c * n_tiles);
@@ -223,6 +226,37 @@ analog_kernel(const AnalogParams a) {
     if (KREG == 0) for (int i = 0; i < k; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
     double worst = INFINITY;                          // current k-th best distance
     float worstf = INFINITY;                          // float32 upper bound of it (relative slack 1e-6 >> float32 error)
+    int qn = 0;                                       // candidates parked in this lane's queue
+
+    // insert the parked candidates, oldest first (keeps "lowest index first on ties"); every lane of
+    // the warp walks the same number of rounds
+    auto drain = [&]() {
+        for (int i = 0; __any_sync(0xffffffffu, i < qn); ++i) {
+            if (i < qn) {
+                const double d = qd[i * AN_THREADS + threadIdx.x];
+                const int id = qi[i * AN_THREADS + threadIdx.x];
+                if (d < worst) {
+                    // branch-free insertion into the register list (strict < keeps the earlier index first on ties)
+#pragma unroll
+                    for (int j = (KREG > 0 ? KREG : 1) - 1; j > 0; --j) {
+                        const bool shift = d < bd[j - 1];
+                        const bool here = !shift && (d < bd[j]);
+                        const double nd = shift ? bd[j - 1] : (here ? d : bd[j]);
+                        const int ni = shift ? bi[j - 1] : (here ? id : bi[j]);
+                        bd[j] = nd; bi[j] = ni;
+                    }
+                    if (d < bd[0]) { bd[0] = d; bi[0] = id; }
+                    // k may be smaller than KREG: the k-th entry is the acceptance bound
+                    double w = bd[(KREG > 0 ? KREG : 1) - 1];
+#pragma unroll
+                    for (int j = 0; j < (KREG > 0 ? KREG : 1); ++j) if (j == k - 1) w = bd[j];
+                    worst = w;
+                }
+            }
+        }
+        worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
+        qn = 0;
+    };
 
     for (int t0 = 0; t0 < a.t_fit; t0 += AN_CHUNK) {
         const int nt = min(AN_CHUNK, a.t_fit - t0);
@@ -248,8 +282,9 @@ analog_kernel(const AnalogParams a) {
             }
         }
         __syncthreads();
-        if (!live) continue;
+        if (KREG == 0 && !live) continue;
         for (int t = 0; t < nt; ++t) {
+            bool pass = live;
             if (FILTER) {
                 // float32 lower-bound test: the exact float64 distance is only evaluated for the few
                 // points that could enter the list (d32 <= worst * (1 + 1e-6) whenever d64 < worst)
@@ -260,53 +295,49 @@ analog_kernel(const AnalogParams a) {
                     const float d0 = xqf[f4] - cf.x, d1 = xqf[f4 + 1] - cf.y, d2 = xqf[f4 + 2] - cf.z, d3 = xqf[f4 + 3] - cf.w;
                     d32 = fmaf(d0, d0, d32); d32 = fmaf(d1, d1, d32); d32 = fmaf(d2, d2, d32); d32 = fmaf(d3, d3, d32);
                 }
-                if (!(d32 <= worstf)) continue;
+                pass = pass && (d32 <= worstf);
             }
-            double d = 0.0;
+            if (pass) {
+                double d = 0.0;
 #pragma unroll
-            for (int f = 0; f < P; ++f) {
-                if (f < p) { const double tmp = xq[f] - chunk[t * P + f]; d += tmp * tmp; }
-            }
-            if (d < worst) {
-                const int id = t0 + t;
-                if (KREG > 0) {
-                    // branch-free insertion into the register list (strict < keeps the earlier index first on ties)
-#pragma unroll
-                    for (int i = KREG - 1; i > 0; --i) {
-                        const bool shift = d < bd[i - 1];
-                        const bool here = !shift && (d < bd[i]);
-                        const double nd = shift ? bd[i - 1] : (here ? d : bd[i]);
-                        const int ni = shift ? bi[i - 1] : (here ? id : bi[i]);
-                        bd[i] = nd; bi[i] = ni;
-                    }
-                    if (d < bd[0]) { bd[0] = d; bi[0] = id; }
-                    // k may be smaller than KREG: the k-th entry is the acceptance bound
-                    double w = bd[KREG - 1];
-#pragma unroll
-                    for (int i = 0; i < KREG; ++i) if (i == k - 1) w = bd[i];
-                    worst = w;
-                } else {
-                    // large k: binary max-heap on (distance, index) in local memory — O(log k) per accepted
-                    // point instead of shifting a sorted list.  d < root is strict, so a later point at
-                    // the same distance never evicts an earlier one (lowest index first on ties).
-                    int pos = 0;
-                    while (true) {
-                        const int l = 2 * pos + 1;
-                        if (l >= k) break;
-                        const int r = l + 1;
-                        int big = l;
-                        if (r < k && (bd[l] < bd[r] || (bd[l] == bd[r] && bi[l] < bi[r]))) big = r;
-                        if (!(d < bd[big] || (d == bd[big] && id < bi[big]))) break;
-                        bd[pos] = bd[big]; bi[pos] = bi[big];
-                        pos = big;
-                    }
-                    bd[pos] = d; bi[pos] = id;
-                    worst = bd[0];
+                for (int f = 0; f < P; ++f) {
+                    if (f < p) { const double tmp = xq[f] - chunk[t * P + f]; d += tmp * tmp; }
                 }
-                worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
+                if (d < worst) {
+                    const int id = t0 + t;
+                    if (KREG > 0) {
+                        // park the candidate: the (long, branch-free) list insertion runs for the whole
+                        // warp, so it is batched — one pass inserts up to one candidate for every lane
+                        qd[qn * AN_THREADS + threadIdx.x] = d;
+                        qi[qn * AN_THREADS + threadIdx.x] = id;
+                        ++qn;
+                    } else {
+                        // large k: binary max-heap on (distance, index) in local memory — O(log k) per accepted
+                        // point instead of shifting a sorted list.  d < root is strict, so a later point at
+                        // the same distance never evicts an earlier one (lowest index first on ties).
+                        int pos = 0;
+                        while (true) {
+                            const int l = 2 * pos + 1;
+                            if (l >= k) break;
+                            const int r = l + 1;
+                            int big = l;
+                            if (r < k && (bd[l] < bd[r] || (bd[l] == bd[r] && bi[l] < bi[r]))) big = r;
+                            if (!(d < bd[big] || (d == bd[big] && id < bi[big]))) break;
+                            bd[pos] = bd[big]; bi[pos] = bi[big];
+                            pos = big;
+                        }
+                        bd[pos] = d; bi[pos] = id;
+                        worst = bd[0];
+                        worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
+                    }
+                }
+            }
+            if (KREG > 0) {
+                if (__any_sync(0xffffffffu, qn == AN_QD)) drain();
             }
         }
     }
+    if (KREG > 0) drain();
     if (!live) return;
     if (KREG == 0) {
         // heap → ascending (distance, index) order, in place

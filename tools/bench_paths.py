@@ -46,7 +46,14 @@ def report(name, cells, steps_t, ms, alg_bytes, extra=None):
 
 
 def main():
+    only_analog = '--analog' in sys.argv
     gen = torch.Generator(device=dev).manual_seed(0)
+    if not only_analog:
+        qm_paths(gen)
+    analog_paths(gen)
+
+
+def qm_paths(gen):
 
     # config 2: QuantileMapper, whole series as one group (generic 16384-point kernel)
     T, C = 10950, 10000
@@ -91,6 +98,8 @@ def main():
     del xtr, ytr, xp, out
     torch.cuda.empty_cache()
 
+
+def analog_paths(gen):
     # config 4/5 style: analog models, k = 10, 3 predictors
     for name, model, T, Tq, C in (('PureAnalog(k=10, mean_analogs) 1024 cells x 18250', PureAnalog(n_analogs=10, kind='mean_analogs'), 18250, 18250, 1024),
                                   ('AnalogRegression(k=10) 1024 cells x 10950', AnalogRegression(n_analogs=10), 10950, 10950, 1024),
