@@ -207,16 +207,19 @@ analog_kernel(const AnalogParams a) {
     const T* Xq = (const T*)a.Xq;
     const int q = tile * AN_THREADS + threadIdx.x;
     const bool live = q < a.t_query;
-    double xq[P];
+    // the query point: float32 inputs are held as float32 only (the exact float64 value is its
+    // widening), float64 inputs as float64
+    double xq64[FILTER ? 1 : P];
     float xqf[PF];
 #pragma unroll
     for (int f = 0; f < PF; ++f) xqf[f] = 0.0f;
 #pragma unroll
     for (int f = 0; f < P; ++f) {
-        xq[f] = (live && f < p) ? (double)Xq[((int64_t)q * a.p + f) * a.ld + c] : 0.0;
-        xqf[f] = (float)xq[f];
-        if (live && f < p && a.nonfinite && !isfinite(xq[f])) atomicOr(a.nonfinite, 1);
+        const T raw = (live && f < p) ? Xq[((int64_t)q * a.p + f) * a.ld + c] : (T)0;
+        if (FILTER) xqf[f] = (float)raw; else xq64[FILTER ? 0 : f] = (double)raw;
+        if (live && f < p && a.nonfinite && !isfinite((double)raw)) atomicOr(a.nonfinite, 1);
     }
+    auto xqv = [&](int f) -> double { return FILTER ? (double)xqf[f] : xq64[FILTER ? 0 : f]; };
     // running top-k, ascending by (distance, index)
     constexpr int KL = (KREG > 0) ? KREG : SDB_MAX_ANALOGS;
     double bd[KL];
@@ -225,7 +228,7 @@ analog_kernel(const AnalogParams a) {
     for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) { bd[i] = INFINITY; bi[i] = -1; }
     if (KREG == 0) for (int i = 0; i < k; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
     double worst = INFINITY;                          // current k-th best distance
-    float worstf = INFINITY;                          // float32 upper bound of it (relative slack 1e-6 >> float32 error)
+    float worstf = live ? INFINITY : -1.0f;           // float32 upper bound of it (relative slack 1e-6 >> float32 error); lanes without a query never pass
     int qn = 0;                                       // candidates parked in this lane's queue
 
     // insert the parked candidates, oldest first (keeps "lowest index first on ties"); every lane of
@@ -254,7 +257,7 @@ analog_kernel(const AnalogParams a) {
                 }
             }
         }
-        worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
+        if (live) worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
         qn = 0;
     };
 
@@ -283,57 +286,92 @@ analog_kernel(const AnalogParams a) {
         }
         __syncthreads();
         if (KREG == 0 && !live) continue;
-        for (int t = 0; t < nt; ++t) {
-            bool pass = live;
-            if (FILTER) {
-                // float32 lower-bound test: the exact float64 distance is only evaluated for the few
-                // points that could enter the list (d32 <= worst * (1 + 1e-6) whenever d64 < worst)
-                float d32 = 0.0f;
+        // exact float64 distance of training point t (same operation order as the reference's KDTree)
+        auto exact_d = [&](int t) -> double {
+            double d = 0.0;
 #pragma unroll
-                for (int f4 = 0; f4 < PF; f4 += 4) {
-                    const float4 cf = *reinterpret_cast<const float4*>(&chunkf[t * PF + f4]);
-                    const float d0 = xqf[f4] - cf.x, d1 = xqf[f4 + 1] - cf.y, d2 = xqf[f4 + 2] - cf.z, d3 = xqf[f4 + 3] - cf.w;
-                    d32 = fmaf(d0, d0, d32); d32 = fmaf(d1, d1, d32); d32 = fmaf(d2, d2, d32); d32 = fmaf(d3, d3, d32);
-                }
-                pass = pass && (d32 <= worstf);
+            for (int f = 0; f < P; ++f) {
+                if (f < p) { const double tmp = xqv(f) - chunk[t * P + f]; d += tmp * tmp; }
             }
-            if (pass) {
-                double d = 0.0;
-#pragma unroll
-                for (int f = 0; f < P; ++f) {
-                    if (f < p) { const double tmp = xq[f] - chunk[t * P + f]; d += tmp * tmp; }
+            return d;
+        };
+        auto accept = [&](int t, double d) {
+            const int id = t0 + t;
+            if (KREG > 0) {
+                // park the candidate: the (long, branch-free) list insertion runs for the whole warp,
+                // so it is batched — one pass inserts up to one candidate for every lane
+                qd[qn * AN_THREADS + threadIdx.x] = d;
+                qi[qn * AN_THREADS + threadIdx.x] = id;
+                ++qn;
+            } else {
+                // large k: binary max-heap on (distance, index) in local memory — O(log k) per accepted
+                // point.  d < root is strict, so a later point at the same distance never evicts an
+                // earlier one (lowest index first on ties).
+                int pos = 0;
+                while (true) {
+                    const int l = 2 * pos + 1;
+                    if (l >= k) break;
+                    const int r = l + 1;
+                    int big = l;
+                    if (r < k && (bd[l] < bd[r] || (bd[l] == bd[r] && bi[l] < bi[r]))) big = r;
+                    if (!(d < bd[big] || (d == bd[big] && id < bi[big]))) break;
+                    bd[pos] = bd[big]; bi[pos] = bi[big];
+                    pos = big;
                 }
-                if (d < worst) {
-                    const int id = t0 + t;
-                    if (KREG > 0) {
-                        // park the candidate: the (long, branch-free) list insertion runs for the whole
-                        // warp, so it is batched — one pass inserts up to one candidate for every lane
-                        qd[qn * AN_THREADS + threadIdx.x] = d;
-                        qi[qn * AN_THREADS + threadIdx.x] = id;
-                        ++qn;
-                    } else {
-                        // large k: binary max-heap on (distance, index) in local memory — O(log k) per accepted
-                        // point instead of shifting a sorted list.  d < root is strict, so a later point at
-                        // the same distance never evicts an earlier one (lowest index first on ties).
-                        int pos = 0;
-                        while (true) {
-                            const int l = 2 * pos + 1;
-                            if (l >= k) break;
-                            const int r = l + 1;
-                            int big = l;
-                            if (r < k && (bd[l] < bd[r] || (bd[l] == bd[r] && bi[l] < bi[r]))) big = r;
-                            if (!(d < bd[big] || (d == bd[big] && id < bi[big]))) break;
-                            bd[pos] = bd[big]; bi[pos] = bi[big];
-                            pos = big;
+                bd[pos] = d; bi[pos] = id;
+                worst = bd[0];
+                worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
+            }
+        };
+        if (FILTER) {
+            // float32 lower-bound test, four training points per round: the exact float64 distance is
+            // only evaluated for the few points that could enter the list (d32 <= worst * (1 + 1e-6)
+            // whenever d64 < worst).  The queue (depth 8) is drained when a lane holds more than 4.
+            const float4* cf4 = reinterpret_cast<const float4*>(chunkf);
+            for (int tb = 0; tb < nt; tb += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = tb + u;
+                    if (t < nt) {
+                        float d32;
+                        if (PF == 4) {
+                            const float4 cf = cf4[t];
+                            const float d0 = xqf[0] - cf.x;
+                            d32 = d0 * d0;
+                            if (P > 1) { const float d1 = xqf[1] - cf.y; d32 = fmaf(d1, d1, d32); }
+                            if (P > 2) { const float d2 = xqf[2] - cf.z; d32 = fmaf(d2, d2, d32); }
+                            if (P > 3) { const float d3 = xqf[3] - cf.w; d32 = fmaf(d3, d3, d32); }
+                        } else {
+                            const float4 ca = cf4[2 * t], cb = cf4[2 * t + 1];
+                            const float d0 = xqf[0] - ca.x, d1 = xqf[1] - ca.y, d2 = xqf[2] - ca.z, d3 = xqf[3] - ca.w;
+                            const float d4 = xqf[4] - cb.x, d5 = xqf[5] - cb.y, d6 = xqf[6] - cb.z, d7 = xqf[7] - cb.w;
+                            d32 = d0 * d0;
+                            d32 = fmaf(d1, d1, d32); d32 = fmaf(d2, d2, d32); d32 = fmaf(d3, d3, d32);
+                            d32 = fmaf(d4, d4, d32); d32 = fmaf(d5, d5, d32); d32 = fmaf(d6, d6, d32); d32 = fmaf(d7, d7, d32);
                         }
-                        bd[pos] = d; bi[pos] = id;
-                        worst = bd[0];
-                        worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
+                        if (d32 <= worstf) {
+                            const double d = exact_d(t);
+                            if (d < worst) accept(t, d);
+                        }
                     }
                 }
+                if (KREG > 0) {
+                    if (__any_sync(0xffffffffu, qn > AN_QD - 4)) drain();
+                }
             }
-            if (KREG > 0) {
-                if (__any_sync(0xffffffffu, qn == AN_QD)) drain();
+        } else {
+            for (int tb = 0; tb < nt; tb += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int t = tb + u;
+                    if (t < nt && live) {
+                        const double d = exact_d(t);
+                        if (d < worst) accept(t, d);
+                    }
+                }
+                if (KREG > 0) {
+                    if (__any_sync(0xffffffffu, qn > AN_QD - 4)) drain();
+                }
             }
         }
     }
@@ -374,11 +412,17 @@ analog_kernel(const AnalogParams a) {
         for (int i = 0; i < KREG; ++i) { li[i] = bi[i]; ld2[i] = bd[i]; }
         auto idx = [&](int i) -> int { return li[i]; };
         auto dist2 = [&](int i) -> double { return ld2[i]; };
+        double xq[P];
+#pragma unroll
+        for (int f = 0; f < P; ++f) xq[f] = xqv(f);
         if (a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<T, P>(a, q, c, k, idx, xq);
         else pure_analog_epilogue<T>(a, q, c, k, idx, dist2);
     } else {
         auto idx = [&](int i) -> int { return bi[i]; };
         auto dist2 = [&](int i) -> double { return bd[i]; };
+        double xq[P];
+#pragma unroll
+        for (int f = 0; f < P; ++f) xq[f] = xqv(f);
         if (a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<T, P>(a, q, c, k, idx, xq);
         else pure_analog_epilogue<T>(a, q, c, k, idx, dist2);
     }
