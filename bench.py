@@ -190,6 +190,19 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
+def ncu_traffic(kernel: str, units: float):
+    """DRAM bytes per launch of ``kernel`` from the committed ncu capture (profiles/r01_traffic.json),
+    scaled to this run's number of cell-timesteps per launch (traffic is linear in it)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+            t = json.load(f)
+        k = t['kernels'][kernel]
+        per_unit = (k['dram_bytes_read'] + k['dram_bytes_write']) / (t['cells'] * t['days'])
+        return per_unit * units
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -351,7 +364,9 @@ def run_b200(a):
             'gather': gather,
             'gpu_launches': 4 * a.steps,
             'roofline': {'bound': 'hbm', 'kernel': 'qm_predict_tile_kernel<32,true> (dominant)', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                         'frac': ach / peak, 'traffic': None, 'peak_source': peak_src,
+                         'frac': ach / peak, 'traffic': ncu_traffic('qm_predict_tile_kernel<32,true>', float(C) * T),
+                         'traffic_source': 'profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)',
+                         'peak_source': peak_src,
                          'algorithmic_bytes_per_cell_timestep': ALG_BYTES_PREDICT, 'kernel_ms': pms,
                          'whole_step': {'achieved': ach_step, 'frac': ach_step / peak,
                                         'algorithmic_bytes_per_cell_timestep': ALG_BYTES_STEP}},
