@@ -34,7 +34,7 @@ __device__ __forceinline__ int skew(int j) { return j + (j >> 5); }
 template <int E>
 constexpr size_t fit_tile_smem() { return (size_t)TILE_CT * TileGeom<E>::NPS * 4; }
 template <int E>
-constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 2 * TileGeom<E>::NPS * 4; }
+constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 2 * TileGeom<E>::NPS * 4 + (size_t)TileGeom<E>::NP * 4; }
 
 // cooperative, coalesced load of one group's rows for the CTA's 8 cells into tile[cell][skew(j)].
 // cp.async (LDGSTS): every thread fires all its row segments back to back, no register staging;
@@ -42,21 +42,26 @@ constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 2 * TileGeom<E>:
 template <int E>
 __device__ __forceinline__ void issue_tile_load(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
                                                 int64_t c0, const int32_t* __restrict__ rg, int n,
-                                                const uint8_t* __restrict__ valid) {
+                                                const uint8_t* __restrict__ valid, int32_t* rowtab = nullptr) {
     constexpr int NPS = TileGeom<E>::NPS;
     const int cc = threadIdx.x & (TILE_CT - 1);
     const int64_t c = c0 + cc;
     const bool ok = c < C && (!valid || valid[c]);
     float* dst = tile + cc * NPS;
     const float* col = src + c;
-    if (ok) {
-#pragma unroll 4
-        for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT) {
+    // the row numbers are loaded eight at a time (independent global loads), then the copies fire;
+    // they are also left in shared memory for the store pass (rowtab), which then needs no global
+    // index loads at all
+#pragma unroll 8
+    for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT) {
+        const int32_t row = __ldg(rg + j);
+        if (rowtab && cc == 0) rowtab[j] = row;
+        if (ok) {
             const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst + skew(j));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(saddr), "l"(col + (int64_t)rg[j] * ld) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(saddr), "l"(col + (int64_t)row * ld) : "memory");
+        } else {
+            dst[skew(j)] = 0.0f;
         }
-    } else {
-        for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT) dst[skew(j)] = 0.0f;
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
@@ -66,8 +71,8 @@ __device__ __forceinline__ void wait_tile_loads() { asm volatile("cp.async.wait_
 template <int E>
 __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
                                           int64_t c0, const int32_t* __restrict__ rg, int n,
-                                          const uint8_t* __restrict__ valid) {
-    issue_tile_load<E>(tile, src, ld, C, c0, rg, n, valid);
+                                          const uint8_t* __restrict__ valid, int32_t* rowtab = nullptr) {
+    issue_tile_load<E>(tile, src, ld, C, c0, rg, n, valid, rowtab);
     wait_tile_loads<0>();
 }
 
@@ -456,16 +461,16 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
 // coalesced store of one output tile (rows of 8 cells)
 template <int E>
 __device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictParams& p, int64_t c0,
-                                           const int32_t* __restrict__ rg, int n) {
+                                           const int32_t* rowtab, int n) {
     constexpr int NPS = TileGeom<E>::NPS;
     const int cc = threadIdx.x & (TILE_CT - 1);
     const int64_t cs = c0 + cc;
     if (cs < p.C) {
         float* outp = (float*)p.out + cs;
         const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
-#pragma unroll 4
+#pragma unroll 8
         for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT)
-            __stcs(outp + (int64_t)rg[j] * p.ld_out, srcp[skew(j)]);
+            __stcs(outp + (int64_t)rowtab[j] * p.ld_out, srcp[skew(j)]);
     }
 }
 
@@ -477,6 +482,7 @@ qm_predict_tile_kernel(const PredictParams p) {
     extern __shared__ uint32_t smem_u[];
     float* tileX = reinterpret_cast<float*>(smem_u);                        // inputs of the group
     uint32_t* tileR = smem_u + TILE_CT * NPS;                               // shift → outputs (float bits)
+    int32_t* rowtab = reinterpret_cast<int32_t*>(smem_u + 2 * TILE_CT * NPS);   // row numbers of the group
     const int g = blockIdx.y;
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
     const int n = p.len[g];
@@ -496,7 +502,7 @@ qm_predict_tile_kernel(const PredictParams p) {
         // the fitted sorted values are wanted right after the sort: pull the record into L2 now
         if (lane * 32 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(S + lane * 32));
     }
-    load_tile<E>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid);
+    load_tile<E>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid, rowtab);
     __syncthreads();
     uint32_t* R = tileR + warp * NPS;
     if (in_range && !active) {
@@ -505,7 +511,7 @@ qm_predict_tile_kernel(const PredictParams p) {
         map_cell_group<E, SHIFT>(p, tileX + warp * NPS, R, lane, c, n, m, rg, S, (double)xc_f, (double)yc_f);
     }
     __syncthreads();
-    store_tile<E>(tileR, p, c0, rg, n);
+    store_tile<E>(tileR, p, c0, rowtab, n);
 }
 
 // grid = (cell tiles): the CTA walks all groups of its 8 cells; the next group's tile is in flight
@@ -518,6 +524,8 @@ qm_predict_tile_pipe_kernel(const PredictParams p) {
     float* tileX0 = reinterpret_cast<float*>(smem_u);
     float* tileX1 = tileX0 + TILE_CT * NPS;
     uint32_t* tileR = smem_u + 2 * TILE_CT * NPS;
+    int32_t* rowtab0 = reinterpret_cast<int32_t*>(smem_u + 3 * TILE_CT * NPS);
+    int32_t* rowtab1 = rowtab0 + TileGeom<E>::NP;
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = c0 + warp;
@@ -525,7 +533,7 @@ qm_predict_tile_pipe_kernel(const PredictParams p) {
     const bool active = in_range && (!p.valid || p.valid[c]);
     const int G = p.n_groups;
     const float* X = (const float*)p.X;
-    issue_tile_load<E>(tileX0, X, p.ld, p.C, c0, p.rows, p.len[0], p.valid);
+    issue_tile_load<E>(tileX0, X, p.ld, p.C, c0, p.rows, p.len[0], p.valid, rowtab0);
     for (int g = 0; g < G; ++g) {
         float* cur = (g & 1) ? tileX1 : tileX0;
         float* nxt = (g & 1) ? tileX0 : tileX1;
@@ -541,7 +549,8 @@ qm_predict_tile_pipe_kernel(const PredictParams p) {
             if (lane * 32 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(S + lane * 32));
         }
         if (g + 1 < G) {
-            issue_tile_load<E>(nxt, X, p.ld, p.C, c0, p.rows + (int64_t)(g + 1) * p.max_len, p.len[g + 1], p.valid);
+            issue_tile_load<E>(nxt, X, p.ld, p.C, c0, p.rows + (int64_t)(g + 1) * p.max_len, p.len[g + 1], p.valid,
+                               (g & 1) ? rowtab0 : rowtab1);
             wait_tile_loads<1>();
         } else {
             wait_tile_loads<0>();
@@ -554,7 +563,8 @@ qm_predict_tile_pipe_kernel(const PredictParams p) {
             map_cell_group<E, SHIFT>(p, cur + warp * NPS, R, lane, c, n, m, rg, S, (double)xc_f, (double)yc_f);
         }
         __syncthreads();
-        store_tile<E>(tileR, p, c0, rg, n);
+        store_tile<E>(tileR, p, c0, (g & 1) ? rowtab1 : rowtab0, n);
+        __syncthreads();                 // the row table of group g is rewritten by the load of group g+2
     }
 }
 
@@ -575,7 +585,7 @@ template <int E, bool SHIFT>
 static int launch_predict_tile(const PredictParams& p, cudaStream_t st, bool pipelined) {
     if (pipelined) {
         auto kern = qm_predict_tile_pipe_kernel<E, SHIFT>;
-        const size_t smem = (size_t)TILE_CT * 3 * TileGeom<E>::NPS * 4;
+        const size_t smem = (size_t)TILE_CT * 3 * TileGeom<E>::NPS * 4 + 2 * (size_t)TileGeom<E>::NP * 4;
         if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT));
         kern<<<grid, TILE_THREADS, smem, st>>>(p);
