@@ -24,12 +24,15 @@ constexpr int TILE_LMAX = 16;       // longest same-bucket run fixed up locally
 
 template <int E> struct TileGeom {
     static constexpr int NP = 32 * E;
-    static constexpr int NPS = NP + NP / 32 + 4;       // padded row: conflict-free for every access pattern used
+    // padded row: 8 words in front (members -4..-1 of the rolling window read as zeros), one extra word
+    // per 32 members (skew), room for members n..n+4 behind; NPS mod 32 is 4 (E=32) / 28 (E=8) so the
+    // eight rows of a tile start in different banks — conflict-free for every access pattern used
+    static constexpr int NPS = (E == 32) ? 1092 : 284;
     static constexpr int LOG = (E == 8) ? 8 : 10;
     static constexpr uint32_t QMAX = (1u << (32 - LOG)) - 1u;   // bucket of the padding items
     static_assert(E == 8 || E == 32, "tile kernels are instantiated for NP = 256 and 1024");
 };
-__device__ __forceinline__ int skew(int j) { return j + (j >> 5); }
+__device__ __forceinline__ int skew(int j) { return j + (j >> 5) + 8; }      // valid for j >= -8
 
 template <int E>
 constexpr size_t fit_tile_smem() { return (size_t)TILE_CT * TileGeom<E>::NPS * 4; }
@@ -49,6 +52,12 @@ __device__ __forceinline__ void issue_tile_load(float* tile, const float* __rest
     const bool ok = c < C && (!valid || valid[c]);
     float* dst = tile + cc * NPS;
     const float* col = src + c;
+    // zeros around the group: members -4..-1 and n..n+4 of every row (the rolling window reads them
+    // unconditionally)
+    for (int i = threadIdx.x; i < TILE_CT * 9; i += TILE_THREADS) {
+        const int r = i / 9, k9 = i - r * 9;
+        tile[r * NPS + skew(k9 < 4 ? k9 - 4 : n + k9 - 4)] = 0.0f;
+    }
     // the row numbers are loaded eight at a time (independent global loads), then the copies fire;
     // they are also left in shared memory for the store pass (rowtab), which then needs no global
     // index loads at all
@@ -123,22 +132,21 @@ qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
 }
 
 // ---------------------------------------------------------------- predict helpers
-// sum / cnt for the window counts 5..9, correctly rounded: q0 = sum*rc, one FMA residual
-// correction (Markstein).  cnt == 9 everywhere except the first / last four members of a group.
+// sum / cnt for the window counts 1..9, correctly rounded: q0 = sum * rc with rc = RN(1/cnt), then one
+// exact-residual FMA correction (Markstein) — three FP64 instructions, no division subroutine.
+static __constant__ double RC_TAB[10] = {0.0, 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0, 1.0 / 6.0, 1.0 / 7.0,
+                                         1.0 / 8.0, 1.0 / 9.0};
 __device__ __forceinline__ double div_count(double sum, int cnt) {
-    if (cnt == 9) {
-        const double rc = 1.0 / 9.0;
-        const double q0 = sum * rc;
-        const double r = fma(-q0, 9.0, sum);
-        return fma(r, rc, q0);
-    }
-    return sum / (double)cnt;
+    const double rc = RC_TAB[cnt];
+    const double q0 = sum * rc;
+    const double r = fma(-q0, (double)cnt, sum);
+    return fma(r, rc, q0);
 }
 
-// window bounds of member j inside a group of n
+// members of the centred 9-window of member j that exist inside a group of n
 __device__ __forceinline__ int win_count(int j, int n) {
-    const int lo = j - 4 < 0 ? 0 : j - 4, hi = j + 4 > n - 1 ? n - 1 : j + 4;
-    return hi - lo + 1;
+    const int a = 4 - j, b = j + 5 - n;
+    return 9 - (a > 0 ? a : 0) - (b > 0 ? b : 0);
 }
 
 // exact rank key of member j as the reference computes it: x - (rolling mean - xc) in float64
@@ -263,8 +271,8 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
             const int e = i - HL;                          // member offset inside / around the lane's block
             const int jj = j0 + e;
             // E == 32: the skew step only changes at the block edges → static offsets from the row base
-            const int addr = (E == 32) ? rb + e + (e < 0 ? -1 : (e >= 32 ? 1 : 0)) : skew(jj < 0 ? 0 : jj);
-            xh[i] = (jj >= 0 && jj < n) ? myX[addr] : 0.0f;
+            const int addr = (E == 32) ? rb + e + (e < 0 ? -1 : (e >= 32 ? 1 : 0)) : skew(jj);
+            xh[i] = myX[addr];                              // zeros outside [0, n) by construction of the tile
         }
         float lo32 = INFINITY, hi32 = -INFINITY;
         bool bad = false;
