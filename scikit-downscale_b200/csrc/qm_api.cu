@@ -91,6 +91,7 @@ extern "C" int sdb_qm_fit(const void* y, int dtype, int64_t ld, int64_t n_cells,
     if (!y || !rows || !len || !state_off || !sorted_state) return sdb_fail(SDB_E_INVALID, "sdb_qm_fit: NULL pointer");
     if (n_cells <= 0 || n_groups <= 0 || max_len <= 0 || ld < n_cells || state_ld <= 0)
         return sdb_fail(SDB_E_INVALID, "sdb_qm_fit: bad shape");
+    if (ld >= (1LL << 32)) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_qm_fit: row stride must be below 2^32 elements");
     if (dtype != SDB_F32 && dtype != SDB_F64) return sdb_fail(SDB_E_INVALID, "sdb_qm_fit: bad dtype %d", dtype);
     FitParams f{y, ld, n_cells, rows, len, state_off, n_groups, max_len, sorted_state, state_ld, cell_valid, nonfinite};
     cudaStream_t st = (cudaStream_t)stream;
@@ -120,6 +121,7 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
         return sdb_fail(SDB_E_INVALID, "sdb_qm_predict: NULL pointer");
     if (n_cells <= 0 || n_groups <= 0 || max_len <= 0 || max_fit_len <= 0 || ld < n_cells || ld_out < n_cells)
         return sdb_fail(SDB_E_INVALID, "sdb_qm_predict: bad shape");
+    if (ld >= (1LL << 32) || ld_out >= (1LL << 32)) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_qm_predict: row stride must be below 2^32 elements");
     if (mode != SDB_MODE_QM && mode != SDB_MODE_BCSD_P && mode != SDB_MODE_BCSD_T)
         return sdb_fail(SDB_E_INVALID, "sdb_qm_predict: unknown mode %d", mode);
     if ((dtype != SDB_F32 && dtype != SDB_F64) || (out_dtype != SDB_F32 && out_dtype != SDB_F64))

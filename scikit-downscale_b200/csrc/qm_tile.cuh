@@ -67,7 +67,7 @@ __device__ __forceinline__ void issue_tile_load(float* tile, const float* __rest
         if (rowtab && cc == 0) rowtab[j] = row;
         if (ok) {
             const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst + skew(j));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(saddr), "l"(col + (int64_t)row * ld) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(saddr), "l"(col + (uint64_t)(uint32_t)row * (uint32_t)ld) : "memory");     // 32x32→64-bit multiply (ld < 2^32 checked by the host)
         } else {
             dst[skew(j)] = 0.0f;
         }
@@ -248,18 +248,15 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
     const bool ratio = (p.mode == SDB_MODE_BCSD_P) && p.return_anoms;
     const bool same = (n == m);
 
-    // final value of a member from its mapped value: restore the shift parked in R (float32)
-    // and remove the target climatology (bcsd.py:263,267 / 170-185)
+    // final value of a member from its mapped value (bcsd.py:263,267 / 170-185).  For the shifted
+    // model the float32 term (shift - y_climo) was parked in R; adding the float32 mapped value to it
+    // with one float32 add is the correctly rounded sum of the two.
     auto finish = [&](int member, float val) {
-        double res;
-        if (SHIFT) {
-            res = (double)__uint_as_float(R[skew(member)]) + (double)val;
-            if (p.return_anoms) res = res - yc;
-        } else {
-            res = ratio ? (double)val / yc : (double)val;
-        }
-        R[skew(member)] = __float_as_uint((float)res);
+        const int at = skew(member);
+        if (SHIFT) R[at] = __float_as_uint(__fadd_rn(__uint_as_float(R[at]), val));
+        else       R[at] = __float_as_uint(ratio ? (float)((double)val / yc) : val);
     };
+    const double park_off = (SHIFT && p.return_anoms) ? yc : 0.0;
 
     // ---- 1. own members (+ 4 / 5 halo) to registers; key bounds from the plain value range
     constexpr int HL = SHIFT ? 4 : 0, HR = SHIFT ? 5 : 0;
@@ -306,7 +303,7 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
                     uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
                     q = q > QMAX - 1 ? QMAX - 1 : q;
                     v[e].k = (q << LOG) | (uint32_t)j;
-                    R[rb + e] = __float_as_uint((float)shift);
+                    R[rb + e] = __float_as_uint((float)(shift - park_off));
                 } else {
                     v[e].k = 0xffffffffu;
                 }
@@ -478,7 +475,7 @@ __device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictP
         const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
 #pragma unroll 8
         for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT)
-            __stcs(outp + (int64_t)rowtab[j] * p.ld_out, srcp[skew(j)]);
+            __stcs(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out, srcp[skew(j)]);
     }
 }
 
