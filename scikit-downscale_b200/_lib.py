@@ -11,7 +11,7 @@ import os
 from ctypes import c_char_p, c_double, c_int, c_int64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libsdb.so')
+LIB_PATH = os.environ.get('SDB_LIBRARY') or os.path.join(_HERE, 'csrc', 'libsdb.so')   # SDB_LIBRARY: experiment builds
 
 SDB_F32, SDB_F64 = 0, 1
 MODE_QM, MODE_BCSD_P, MODE_BCSD_T = 0, 1, 2

@@ -18,7 +18,10 @@
 
 namespace sdb {
 
-constexpr int TILE_CT = 8;          // cells per CTA (= warps per CTA)
+#ifndef SDB_TILE_CT
+#define SDB_TILE_CT 8
+#endif
+constexpr int TILE_CT = SDB_TILE_CT;   // cells per CTA (= warps per CTA): 8 cells = one 32-byte sector per row
 constexpr int TILE_THREADS = 32 * TILE_CT;
 constexpr int TILE_LMAX = 16;       // longest same-bucket run fixed up locally
 
@@ -27,7 +30,7 @@ template <int E> struct TileGeom {
     // padded row: 8 words in front (members -4..-1 of the rolling window read as zeros), one extra word
     // per 32 members (skew), room for members n..n+4 behind; NPS mod 32 is 4 (E=32) / 28 (E=8) so the
     // eight rows of a tile start in different banks — conflict-free for every access pattern used
-    static constexpr int NPS = (E == 32) ? 1092 : 284;
+    static constexpr int NPS = (TILE_CT == 8) ? ((E == 32) ? 1092 : 284) : ((E == 32) ? 1096 : 296);
     static constexpr int LOG = (E == 8) ? 8 : 10;
     static constexpr uint32_t QMAX = (1u << (32 - LOG)) - 1u;   // bucket of the padding items
     static_assert(E == 8 || E == 32, "tile kernels are instantiated for NP = 256 and 1024");
@@ -62,7 +65,7 @@ __device__ __forceinline__ void issue_tile_load(float* tile, const float* __rest
     // they are also left in shared memory for the store pass (rowtab), which then needs no global
     // index loads at all
 #pragma unroll 8
-    for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT) {
+    for (int j = threadIdx.x / TILE_CT; j < n; j += TILE_THREADS / TILE_CT) {
         const int32_t row = __ldg(rg + j);
         if (rowtab && cc == 0) rowtab[j] = row;
         if (ok) {
@@ -474,14 +477,14 @@ __device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictP
         float* outp = (float*)p.out + cs;
         const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
 #pragma unroll 8
-        for (int j = threadIdx.x >> 3; j < n; j += TILE_THREADS / TILE_CT)
+        for (int j = threadIdx.x / TILE_CT; j < n; j += TILE_THREADS / TILE_CT)
             __stcs(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out, srcp[skew(j)]);
     }
 }
 
 // grid = (cell tiles, groups): one (tile, group) per CTA
 template <int E, bool SHIFT>
-__global__ void __launch_bounds__(TILE_THREADS, 3)
+__global__ void __launch_bounds__(TILE_THREADS, 24 / TILE_CT)
 qm_predict_tile_kernel(const PredictParams p) {
     constexpr int NPS = TileGeom<E>::NPS;
     extern __shared__ uint32_t smem_u[];
