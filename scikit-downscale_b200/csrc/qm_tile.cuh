@@ -90,7 +90,7 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
 
 // ---------------------------------------------------------------- fit
 template <int E>
-__global__ void __launch_bounds__(TILE_THREADS)
+__global__ void __launch_bounds__(TILE_THREADS, 24 / TILE_CT)
 qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
                    const int32_t* __restrict__ rows, const int32_t* __restrict__ len,
                    const int64_t* __restrict__ off, int max_len,
