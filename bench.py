@@ -95,9 +95,10 @@ def cpu_sample(T: int, n_cells: int, cores: int):
 
 
 def cpu_cells(T: int, cores: int, target_seconds: float) -> int:
-    _oracle_cells((T, 0, 1, 1))                         # import + warm-up in this process
-    t1 = _oracle_cells((T, 0, 2, 1)) / 2                # seconds per cell per core
-    per_worker = int(max(1, min(400, target_seconds / max(t1, 1e-4))))
+    """Sample size for about ``target_seconds`` of wall time, calibrated THROUGH the pool (the host
+    cores of a shared box deliver far less in parallel than one process alone suggests)."""
+    _, done, wall = cpu_sample(T, 2 * cores, cores)           # 2 cells per worker
+    per_worker = int(max(2, min(400, 2 * target_seconds / max(wall, 1e-3))))
     return per_worker * cores
 
 
