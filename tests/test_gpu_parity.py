@@ -465,3 +465,53 @@ def test_streamed_host_pipeline_matches_whole_block(dev, model_name):
     bad[7, 50] = np.nan
     with pytest.raises(ValueError, match='NaN'):
         streamed.fit(Xtr, bad, time=idx)
+
+
+# ------------------------------------------------------------------ randomized sweep
+@pytest.mark.parametrize('seed', range(6))
+def test_random_small_cases_vs_oracle(dev, seed):
+    """random shapes / lengths / ties / NaN cells / dtypes through every BCSD + QM entry point;
+    ranks bit-exact, values 1e-5, all kernel families."""
+    rng = np.random.default_rng(1000 + seed)
+    years = int(rng.integers(1, 9))
+    Tf = 365 * years + int(rng.integers(0, 40))
+    Tp = int(rng.integers(20, 3 * Tf))
+    C = int(rng.integers(1, 20))
+    dtype = np.float32 if seed % 3 else np.float64
+    idx_f = synth.daily_index(Tf, '1983-03-05')
+    idx_p = synth.daily_index(Tp, '1990-11-17')
+    Xtr, ytr, _ = synth.temperature(Tf, C, seed=seed, dtype=dtype)
+    _, _, Xp = synth.temperature(Tp, C, seed=seed + 50, dtype=dtype)
+    if seed % 2:                                   # quantised data: plenty of exact ties
+        Xp = (np.round(Xp * 4) / 4).astype(dtype)
+        ytr = (np.round(ytr * 2) / 2).astype(dtype)
+    nan_cells = [c for c in range(C) if rng.random() < 0.15]
+    for c in nan_cells:
+        Xtr[:, c] = np.nan
+    fit_g = oracle.groups_from_keys(oracle.month_keys(idx_f))
+    pred_g = oracle.groups_from_keys(oracle.month_keys(idx_p))
+    for family in ('tile', 'generic', 'pipe'):
+        with force_generic(family):
+            for anoms in (True, False):
+                m = pm().BcsdTemperature(return_anoms=anoms)
+                xtr = eng().as_device(Xtr, dev)
+                m.fit_batched(xtr, eng().as_device(ytr, dev), idx_f, valid=eng().cell_mask(xtr[0]))
+                out, rank = m.predict_batched(eng().as_device(Xp, dev), idx_p, want_rank=True)
+                out, rank = out.cpu().numpy(), rank.cpu().numpy()
+                for c in range(C):
+                    if c in nan_cells:
+                        assert np.isnan(out[:, c]).all()
+                        continue
+                    st = oracle.bcsd_temperature_fit(Xtr[:, c], ytr[:, c], fit_g)
+                    o, r = oracle.bcsd_temperature_predict(st, Xp[:, c], pred_g, pred_g, anoms, return_rank=True)
+                    assert np.array_equal(rank[:, c], r), (family, anoms, c)
+                    assert_close(out[:, c], o.astype(dtype), scale=np.std(ytr[:, c]))
+            # whole-series QuantileMapper on the same data
+            q = pm().QuantileMapper()
+            q.fit_batched(eng().as_device(ytr, dev))
+            qo, qr = q.transform_batched(eng().as_device(Xp, dev), want_rank=True)
+            qo, qr = qo.cpu().numpy(), qr.cpu().numpy()
+            for c in range(0, C, 3):
+                o, r = oracle.quantile_mapper_transform(Xp[:, c], oracle.quantile_mapper_fit(ytr[:, c]), return_rank=True)
+                assert np.array_equal(qr[:, c], r)
+                assert_close(qo[:, c], o.astype(dtype), scale=np.std(ytr[:, c]))
