@@ -57,9 +57,13 @@ __device__ __forceinline__ void issue_tile_load(float* tile, const float* __rest
     const float* col = src + c;
     // zeros around the group: members -4..-1 and n..n+4 of every row (the rolling window reads them
     // unconditionally)
-    for (int i = threadIdx.x; i < TILE_CT * 9; i += TILE_THREADS) {
-        const int r = i / 9, k9 = i - r * 9;
-        tile[r * NPS + skew(k9 < 4 ? k9 - 4 : n + k9 - 4)] = 0.0f;
+    {
+        const int tail = TileGeom<E>::NP + 5 - n;                  // members n .. NP+4 (padding lanes read them too)
+        const int per_row = 4 + tail;
+        for (int i = threadIdx.x; i < TILE_CT * per_row; i += TILE_THREADS) {
+            const int r = i / per_row, k9 = i - r * per_row;
+            tile[r * NPS + skew(k9 < 4 ? k9 - 4 : n + k9 - 4)] = 0.0f;
+        }
     }
     // the row numbers are loaded eight at a time (independent global loads), then the copies fire;
     // they are also left in shared memory for the store pass (rowtab), which then needs no global
@@ -107,31 +111,25 @@ qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = c0 + warp;
     if (c >= C || (valid && !valid[c])) return;
-    float* my = tile_f + warp * G::NPS;
+    float* my = tile_f + warp * G::NPS + skew(lane * E);      // the lane's E members are contiguous: my[e]
+    const int nj = n - lane * E;                               // members of this lane that exist: e < nj
     K32 v[E];
     bool bad = false;
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        const int j = lane * E + e;
-        if (j < n) {
-            const float x = my[skew(j)];
-            bad |= !isfinite(x);
-            v[e] = make_fit_item(x);
-        } else {
-            v[e] = sentinel_item<K32>(j);
-        }
+        const float x = my[e];
+        bad |= (e < nj) && !isfinite(x);
+        v[e].k = (e < nj) ? f32_to_sortable(x + 0.0f) : 0xffffffffu;
     }
     if (bad && nonfinite) atomicOr(nonfinite, 1);
     sort_blocked<K32, E, 32>(v, lane, nullptr);
     __syncwarp();
 #pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int j = lane * E + e;
-        if (j < n) my[skew(j)] = fit_item_value(v[e]);
-    }
+    for (int e = 0; e < E; ++e) my[e] = sortable_to_f32(v[e].k);       // positions >= n hold padding, never stored
     __syncwarp();
     float* dst = state + c * state_ld + off[g];
-    for (int j = lane; j < n; j += 32) dst[j] = my[skew(j)];      // 128-byte coalesced rows of the cell record
+    const float* row = tile_f + warp * G::NPS;
+    for (int j = lane; j < n; j += 32) dst[j] = row[skew(j)];      // 128-byte coalesced rows of the cell record
 }
 
 // ---------------------------------------------------------------- predict helpers
@@ -140,7 +138,7 @@ qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
 static __constant__ double RC_TAB[10] = {0.0, 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0, 1.0 / 6.0, 1.0 / 7.0,
                                          1.0 / 8.0, 1.0 / 9.0};
 __device__ __forceinline__ double div_count(double sum, int cnt) {
-    const double rc = RC_TAB[cnt];
+    const double rc = (cnt == 9) ? (1.0 / 9.0) : RC_TAB[cnt];
     const double q0 = sum * rc;
     const double r = fma(-q0, (double)cnt, sum);
     return fma(r, rc, q0);
@@ -150,6 +148,15 @@ __device__ __forceinline__ double div_count(double sum, int cnt) {
 __device__ __forceinline__ int win_count(int j, int n) {
     const int a = 4 - j, b = j + 5 - n;
     return 9 - (a > 0 ? a : 0) - (b > 0 ? b : 0);
+}
+
+// rolling mean - xc of a member within 4 of either end of its group (window shorter than 9):
+// direct sum and a true division, out of line — the hot loop only handles full windows
+static __device__ __noinline__ double edge_shift(const float* myX, int n, int j, double xc) {
+    double acc = 0.0;
+    const int lo = j - 4 < 0 ? 0 : j - 4, hi = j + 4 > n - 1 ? n - 1 : j + 4;
+    for (int jj = lo; jj <= hi; ++jj) acc += (double)myX[skew(jj)];
+    return acc / (double)(hi - lo + 1) - xc;
 }
 
 // exact rank key of member j as the reference computes it: x - (rolling mean - xc) in float64
@@ -247,6 +254,7 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
     constexpr uint32_t IDX = (1u << LOG) - 1u;
     const int j0 = lane * E;
     const int j1 = (j0 + E < n) ? j0 + E : n;
+    const int nj = n - j0;                     // members of this lane that exist: e < nj
     const int rb = skew(j0);
     const bool ratio = (p.mode == SDB_MODE_BCSD_P) && p.return_anoms;
     const bool same = (n == m);
@@ -274,17 +282,14 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
             const int addr = (E == 32) ? rb + e + (e < 0 ? -1 : (e >= 32 ? 1 : 0)) : skew(jj);
             xh[i] = myX[addr];                              // zeros outside [0, n) by construction of the tile
         }
-        float lo32 = INFINITY, hi32 = -INFINITY;
-        bool bad = false;
+        float lo32 = INFINITY, hi32 = -INFINITY, nanacc = 0.0f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
-            if (j0 + e < n) {
-                const float x = xh[e + HL];
-                lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x);
-                bad |= !isfinite(x);
-            }
+            const float x = xh[e + HL];
+            if (e < nj) { lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x); }
+            nanacc = fmaf(x, 0.0f, nanacc);                 // NaN / inf anywhere → NaN (padding members are zeros)
         }
-        if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
+        if (nanacc != nanacc && p.nonfinite) atomicOr(p.nonfinite, 1);
         lo32 = warp_min(lo32); hi32 = warp_max(hi32);
 
         // ---- 2. exact rank keys → monotone bucket number, packed with the member position.
@@ -297,15 +302,16 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
             double sum = 0.0;
 #pragma unroll
             for (int i = 0; i < 9; ++i) sum += (double)xh[i];
+            const int e_front = 4 - j0, e_back = nj - 4;     // e < e_front or e >= e_back: window cut by a group end
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int j = j0 + e;
-                if (j < n) {
-                    const double shift = div_count(sum, win_count(j, n)) - xc;
+                if (e < nj) {
+                    double shift = div_count(sum, 9) - xc;
+                    if (e < e_front || e >= e_back) shift = edge_shift(myX, n, j0 + e, xc);
                     const double t = (((double)xh[e + 4] - shift) - lo) * scale;
                     uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
                     q = q > QMAX - 1 ? QMAX - 1 : q;
-                    v[e].k = (q << LOG) | (uint32_t)j;
+                    v[e].k = (q << LOG) | (uint32_t)(j0 + e);
                     R[rb + e] = __float_as_uint((float)(shift - park_off));
                 } else {
                     v[e].k = 0xffffffffu;
@@ -318,12 +324,11 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
             const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int j = j0 + e;
-                if (j < n) {
+                if (e < nj) {
                     const float t = (xh[e] - lo32) * scale;
                     uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
                     q = q > QMAX - 1 ? QMAX - 1 : q;
-                    v[e].k = (q << LOG) | (uint32_t)j;
+                    v[e].k = (q << LOG) | (uint32_t)(j0 + e);
                 } else {
                     v[e].k = 0xffffffffu;
                 }
@@ -338,7 +343,7 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-        bm_eq |= ((j0 + e + 1 < n) && ((v[e].k >> LOG) == (kn >> LOG))) ? (1u << e) : 0u;
+        bm_eq |= ((e + 1 < nj) && (((v[e].k ^ kn) >> LOG) == 0u)) ? (1u << e) : 0u;
     }
     __syncwarp();                             // shifts parked in R are visible to every lane
 
