@@ -138,7 +138,7 @@ qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
 static __constant__ double RC_TAB[10] = {0.0, 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0, 1.0 / 6.0, 1.0 / 7.0,
                                          1.0 / 8.0, 1.0 / 9.0};
 __device__ __forceinline__ double div_count(double sum, int cnt) {
-    const double rc = (cnt == 9) ? (1.0 / 9.0) : RC_TAB[cnt];
+    const double rc = RC_TAB[cnt];
     const double q0 = sum * rc;
     const double r = fma(-q0, (double)cnt, sum);
     return fma(r, rc, q0);
@@ -148,15 +148,6 @@ __device__ __forceinline__ double div_count(double sum, int cnt) {
 __device__ __forceinline__ int win_count(int j, int n) {
     const int a = 4 - j, b = j + 5 - n;
     return 9 - (a > 0 ? a : 0) - (b > 0 ? b : 0);
-}
-
-// rolling mean - xc of a member within 4 of either end of its group (window shorter than 9):
-// direct sum and a true division, out of line — the hot loop only handles full windows
-static __device__ __noinline__ double edge_shift(const float* myX, int n, int j, double xc) {
-    double acc = 0.0;
-    const int lo = j - 4 < 0 ? 0 : j - 4, hi = j + 4 > n - 1 ? n - 1 : j + 4;
-    for (int jj = lo; jj <= hi; ++jj) acc += (double)myX[skew(jj)];
-    return acc / (double)(hi - lo + 1) - xc;
 }
 
 // exact rank key of member j as the reference computes it: x - (rolling mean - xc) in float64
@@ -302,12 +293,10 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
             double sum = 0.0;
 #pragma unroll
             for (int i = 0; i < 9; ++i) sum += (double)xh[i];
-            const int e_front = 4 - j0, e_back = nj - 4;     // e < e_front or e >= e_back: window cut by a group end
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 if (e < nj) {
-                    double shift = div_count(sum, 9) - xc;
-                    if (e < e_front || e >= e_back) shift = edge_shift(myX, n, j0 + e, xc);
+                    const double shift = div_count(sum, win_count(j0 + e, n)) - xc;
                     const double t = (((double)xh[e + 4] - shift) - lo) * scale;
                     uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
                     q = q > QMAX - 1 ? QMAX - 1 : q;
