@@ -374,28 +374,49 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
         tie_carry = __shfl_sync(0xffffffffu, first_end, higher ? (__ffs(higher) - 1) : lane);
     }
 
-    if (mode == 0 && same && !p.rank_out && (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0)) {
-        // the common case: one member per bucket, same length — the member at sorted position
-        // pos takes the fitted order statistic S[pos]; the lane's 32 values are 8 vector loads
-        float4 s4[E / 4];
+    // isolated pairs only (no two tie bits adjacent, also across lanes): the register path below can
+    // patch them in place; longer tie runs (e.g. the zeros of precipitation) take the staged loop
+    bool pairs_only = false;
+    if (mode == 2) {
+        const uint32_t nxt_tie0 = __shfl_down_sync(0xffffffffu, bm_tie & 1u, 1);
+        const bool adjacent = ((bm_tie & (bm_tie >> 1)) != 0) || ((lane < 31) && ((bm_tie >> (E - 1)) & 1u) && nxt_tie0);
+        pairs_only = !__any_sync(0xffffffffu, adjacent);
+    }
+    if ((mode == 0 || pairs_only) && same && !p.rank_out && (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0)) {
+        // the common case: same length and (almost) one member per bucket — the member at sorted
+        // position pos takes the fitted order statistic S[pos]; the lane's 32 values are 8 vector loads
+        float sv[E + 1];
 #pragma unroll
         for (int q4 = 0; q4 < E / 4; ++q4) {
             const int pos = j0 + 4 * q4;
-            if (pos + 3 < n) s4[q4] = __ldg(reinterpret_cast<const float4*>(S + pos));
-            else {
-                s4[q4].x = pos < n ? __ldg(S + pos) : 0.0f;
-                s4[q4].y = pos + 1 < n ? __ldg(S + pos + 1) : 0.0f;
-                s4[q4].z = pos + 2 < n ? __ldg(S + pos + 2) : 0.0f;
-                s4[q4].w = 0.0f;
+            if (pos + 3 < n) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(S + pos));
+                sv[4 * q4] = t4.x; sv[4 * q4 + 1] = t4.y; sv[4 * q4 + 2] = t4.z; sv[4 * q4 + 3] = t4.w;
+            } else {
+                sv[4 * q4] = pos < n ? __ldg(S + pos) : 0.0f;
+                sv[4 * q4 + 1] = pos + 1 < n ? __ldg(S + pos + 1) : 0.0f;
+                sv[4 * q4 + 2] = pos + 2 < n ? __ldg(S + pos + 2) : 0.0f;
+                sv[4 * q4 + 3] = 0.0f;
             }
         }
+        if (mode == 0) {
 #pragma unroll
-        for (int q4 = 0; q4 < E / 4; ++q4) {
-            const int pos = j0 + 4 * q4;
-            if (pos < n) finish((int)(v[4 * q4].k & IDX), s4[q4].x);
-            if (pos + 1 < n) finish((int)(v[4 * q4 + 1].k & IDX), s4[q4].y);
-            if (pos + 2 < n) finish((int)(v[4 * q4 + 2].k & IDX), s4[q4].z);
-            if (pos + 3 < n) finish((int)(v[4 * q4 + 3].k & IDX), s4[q4].w);
+            for (int e = 0; e < E; ++e)
+                if (e < nj) finish((int)(v[e].k & IDX), sv[e]);
+        } else {
+            // same scatter with the isolated same-bucket pairs patched: an inverted pair exchanges its
+            // members, an exactly tied pair both take the higher order statistic (tie-max rank)
+            sv[E] = (j0 + E < n) ? __ldg(S + j0 + E) : 0.0f;
+            const uint32_t prv_last_k = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                if (e < nj) {
+                    uint32_t w = v[e].k;
+                    if ((bm_gt >> e) & 1u) w = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
+                    else if ((e == 0) ? prev_gt : ((bm_gt >> (e == 0 ? 0 : e - 1)) & 1u)) w = (e == 0) ? prv_last_k : v[e == 0 ? e : e - 1].k;
+                    finish((int)(w & IDX), ((bm_tie >> e) & 1u) ? sv[e + 1] : sv[e]);
+                }
+            }
         }
     } else if (mode == 3) {
         rank_exact64<E, SHIFT>(myX, n, xc, lane);            // ranks by member → input row
