@@ -86,25 +86,18 @@ __device__ __forceinline__ I keep(const I& v, const I& o, bool lower) {
 }
 
 // ---------------------------------------------------------------- thread-local pieces
-// sort the E items of one thread (levels k = 2 .. E of the mirror network)
+// sort the E items of one thread: Batcher's odd-even merge sort (191 compare-exchanges for
+// E = 32 against 240 for the bitonic network); the network is spelled out in sort_net.inc so
+// every register index is a literal
+#include "sort_net.inc"
 template <class I, int E>
 __device__ __forceinline__ void local_sort(I (&v)[E]) {
-#pragma unroll
-    for (int k = 2; k <= E; k <<= 1) {
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            int p = e ^ (k - 1);
-            if (p > e) cmpswap(v[e], v[p]);
-        }
-#pragma unroll
-        for (int j = k >> 2; j > 0; j >>= 1) {
-#pragma unroll
-            for (int e = 0; e < E; ++e) {
-                int p = e ^ j;
-                if (p > e) cmpswap(v[e], v[p]);
-            }
-        }
-    }
+    static_assert(E == 8 || E == 16 || E == 32, "sorting networks are generated for 8, 16 and 32 items");
+#define SDB_CE(a, b) cmpswap(v[a], v[b]);
+    if constexpr (E == 8) { SDB_SORT_NET_8 }
+    else if constexpr (E == 16) { SDB_SORT_NET_16 }
+    else { SDB_SORT_NET_32 }
+#undef SDB_CE
 }
 // the thread-local half-cleaners j = E/2 .. 1 that finish every wider merge level
 template <class I, int E>
