@@ -186,36 +186,16 @@ def qm_fit_into(st: QMFitted, y: torch.Tensor, X: torch.Tensor | None = None,
     if C != st.n_cells or y.dtype != st.dtype:
         raise ValueError('y does not match the state block')
     rows, length = st.sort_table.device(y.device)
-    # The climatology kernels are HBM-bound, the sort kernel is ALU-bound and neither depends on the
-    # other: they run concurrently on a side stream and join before anything consumes the state.
-    main = torch.cuda.current_stream(y.device)
-    side = _side_stream(y.device)
-    side.wait_stream(main)
-    with torch.cuda.stream(side):
-        if st.y_climo is not None:
-            group_mean(y, st.mean_table, mean_how, st.valid, st.nonfinite, out=st.y_climo)
-        if st.x_climo is not None:
-            if X is None or X.shape != y.shape:
-                raise ValueError('X and y must have the same shape')
-            group_mean(X, st.mean_table, mean_how, st.valid, st.nonfinite, out=st.x_climo)
     _lib.check(lib.sdb_qm_fit(_ptr(y), _code(y), ld, C, _ptr(rows), _ptr(length), _ptr(st.state_off_dev),
                               st.sort_table.n_groups, st.sort_table.rows.shape[1], _ptr(st.sorted_state),
-                              st.state_ld, _ptr(st.valid), _ptr(st.nonfinite), main.cuda_stream), 'sdb_qm_fit')
-    main.wait_stream(side)
-    for t in (y, X, st.y_climo, st.x_climo):
-        if t is not None:
-            t.record_stream(side)
+                              st.state_ld, _ptr(st.valid), _ptr(st.nonfinite), _stream()), 'sdb_qm_fit')
+    if st.y_climo is not None:
+        group_mean(y, st.mean_table, mean_how, st.valid, st.nonfinite, out=st.y_climo)
+    if st.x_climo is not None:
+        if X is None or X.shape != y.shape:
+            raise ValueError('X and y must have the same shape')
+        group_mean(X, st.mean_table, mean_how, st.valid, st.nonfinite, out=st.x_climo)
     return st
-
-
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device) -> torch.cuda.Stream:
-    key = str(device)
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
-    return _SIDE_STREAMS[key]
 
 
 def qm_fit(y: torch.Tensor, sort_table: GroupTable, *, valid=None, X=None, mean_table=None,
