@@ -72,7 +72,8 @@ int sdb_version(void);
 const char* sdb_last_error(void);
 
 /* Testing aid: bit 0 forces the generic (any dtype / any group length) kernels even where the
- * float32 tile kernels apply.  Returns the previous flags. */
+ * float32 tile kernels apply; bit 1 makes the tile kernels use their 4-byte row accesses (the
+ * path rows that are not 16-byte aligned take) everywhere.  Returns the previous flags. */
 int sdb_set_debug_flags(int flags);
 
 /* Strided host<->device copy of a [height, width_bytes] block (cudaMemcpy2DAsync) on `stream`:

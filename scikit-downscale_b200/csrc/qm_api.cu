@@ -55,7 +55,7 @@ static int pick_np(int max_len) {
     return -1;
 }
 
-static int g_debug_flags = 0;      // bit 0: force the generic kernels (testing); bit 1: pipelined predict tile kernel
+static int g_debug_flags = 0;      // bit 0: force the generic kernels; bit 1: tile kernels without 16-byte row accesses (testing)
 
 }  // namespace sdb
 
@@ -93,7 +93,8 @@ extern "C" int sdb_qm_fit(const void* y, int dtype, int64_t ld, int64_t n_cells,
         return sdb_fail(SDB_E_INVALID, "sdb_qm_fit: bad shape");
     if (ld >= (1LL << 32)) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_qm_fit: row stride must be below 2^32 elements");
     if (dtype != SDB_F32 && dtype != SDB_F64) return sdb_fail(SDB_E_INVALID, "sdb_qm_fit: bad dtype %d", dtype);
-    FitParams f{y, ld, n_cells, rows, len, state_off, n_groups, max_len, sorted_state, state_ld, cell_valid, nonfinite};
+    FitParams f{y, ld, n_cells, rows, len, state_off, n_groups, max_len, sorted_state, state_ld, cell_valid, nonfinite,
+                (g_debug_flags & 2) != 0};
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == SDB_F32 && !(g_debug_flags & 1)) {
         if (max_len <= 256) return qm_fit_tile_np256(f, st);
@@ -135,13 +136,13 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
     p.x_climo = x_climo; p.y_climo = y_climo; p.ld_climo = ld_climo; p.return_anoms = return_anoms;
     p.roll_nbr = roll_nbr; p.out = out; p.ld_out = ld_out; p.rank_out = rank_out; p.valid = cell_valid; p.nonfinite = nonfinite;
     p.mode = mode; p.out_f64 = (out_dtype == SDB_F64); p.n_groups = n_groups;
+    p.no_vec = (g_debug_flags & 2) != 0;
     const int kind = (mode != SDB_MODE_BCSD_T) ? KIND_RAW : (roll_nbr ? KIND_SHIFT_TAB : KIND_SHIFT);
     cudaStream_t st = (cudaStream_t)stream;
     const int longest = max_len > max_fit_len ? max_len : max_fit_len;
     if (dtype == SDB_F32 && out_dtype == SDB_F32 && kind != KIND_SHIFT_TAB && longest <= 1024 && !(g_debug_flags & 1)) {
-        const bool pipelined = (g_debug_flags & 2) != 0;
-        if (longest <= 256) return qm_predict_tile_np256(kind, p, st, pipelined);
-        return qm_predict_tile_np1024(kind, p, st, pipelined);
+        if (longest <= 256) return qm_predict_tile_np256(kind, p, st);
+        return qm_predict_tile_np1024(kind, p, st);
     }
     switch (pick_np(max_len)) {
         case 256:   return qm_predict_np256(dtype, kind, p, st);

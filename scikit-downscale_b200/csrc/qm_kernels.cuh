@@ -117,6 +117,7 @@ struct PredictParams {
     int mode;        // SDB_MODE_*
     int out_f64;     // output element type: 0 float, 1 double
     int n_groups;
+    int no_vec;      // testing: tile kernels use the 4-byte (unaligned-safe) row loads and stores
 };
 
 // kernel flavours (compile-time): what the rank keys are
@@ -303,6 +304,7 @@ struct FitParams {
     const void* y; int64_t ld; int64_t C;
     const int32_t* rows; const int32_t* len; const int64_t* off; int n_groups; int max_len;
     void* state; int64_t state_ld; const uint8_t* valid; int32_t* nonfinite;
+    int no_vec;      // testing: see PredictParams
 };
 
 template <typename T, int E, int NT>
@@ -335,8 +337,8 @@ static int launch_predict(const PredictParams& p, cudaStream_t st) {
 // fast tile kernels (qm_tile.cuh), float32 only, instantiated in qm_np256.cu / qm_np1024.cu
 int qm_fit_tile_np256(const FitParams& f, cudaStream_t st);
 int qm_fit_tile_np1024(const FitParams& f, cudaStream_t st);
-int qm_predict_tile_np256(int kind, const PredictParams& p, cudaStream_t st, bool pipelined);
-int qm_predict_tile_np1024(int kind, const PredictParams& p, cudaStream_t st, bool pipelined);
+int qm_predict_tile_np256(int kind, const PredictParams& p, cudaStream_t st);
+int qm_predict_tile_np1024(int kind, const PredictParams& p, cudaStream_t st);
 
 // per-size entry points, defined in qm_np<N>.cu
 #define SDB_DECLARE_SIZE(NP)                                                             \

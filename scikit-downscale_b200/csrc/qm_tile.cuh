@@ -25,6 +25,15 @@ constexpr int TILE_CT = SDB_TILE_CT;   // cells per CTA (= warps per CTA): 8 cel
 constexpr int TILE_THREADS = 32 * TILE_CT;
 constexpr int TILE_LMAX = 16;       // longest same-bucket run fixed up locally
 
+#ifndef SDB_FIT_BATCH
+#define SDB_FIT_BATCH 8
+#endif
+#ifndef SDB_PRED_BATCH
+#define SDB_PRED_BATCH 4
+#endif
+#ifndef SDB_STORE_BATCH
+#define SDB_STORE_BATCH 1
+#endif
 template <int E> struct TileGeom {
     static constexpr int NP = 32 * E;
     // padded row: 8 words in front (members -4..-1 of the rolling window read as zeros), one extra word
@@ -42,54 +51,108 @@ constexpr size_t fit_tile_smem() { return (size_t)TILE_CT * TileGeom<E>::NPS * 4
 template <int E>
 constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 2 * TileGeom<E>::NPS * 4 + (size_t)TileGeom<E>::NP * 4; }
 
-// cooperative, coalesced load of one group's rows for the CTA's 8 cells into tile[cell][skew(j)].
-// cp.async (LDGSTS): every thread fires all its row segments back to back, no register staging;
-// the caller commits / waits, so a tile can be in flight while another one is being processed.
-template <int E>
-__device__ __forceinline__ void issue_tile_load(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
-                                                int64_t c0, const int32_t* __restrict__ rg, int n,
-                                                const uint8_t* __restrict__ valid, int32_t* rowtab = nullptr) {
+// Cooperative, coalesced load of one group's rows for the CTA's 8 cells into tile[cell][skew(j)],
+// transposing on the way.  Fast path: one 16-byte load per (row, 4 cells) — two threads cover the
+// 32-byte row segment — and four conflict-free shared stores; it needs 16-byte aligned rows
+// (ld % 4 == 0, aligned base) and a full tile.  Otherwise one 4-byte load per (row, cell).
+// The row numbers are also left in shared memory (rowtab) for the store pass.
+template <int E, int BATCH>
+__device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
+                                          int64_t c0, const int32_t* __restrict__ rg, int n,
+                                          const uint8_t* __restrict__ valid, bool allow_vec,
+                                          int32_t* rowtab = nullptr) {
     constexpr int NPS = TileGeom<E>::NPS;
-    const int cc = threadIdx.x & (TILE_CT - 1);
-    const int64_t c = c0 + cc;
-    const bool ok = c < C && (!valid || valid[c]);
-    float* dst = tile + cc * NPS;
-    const float* col = src + c;
-    // zeros around the group: members -4..-1 and n..n+4 of every row (the rolling window reads them
-    // unconditionally)
+    static_assert(TILE_CT == 8, "the vector path assumes 8-cell tiles");
+    // zeros around the group: members -4..-1 and n..NP+4 of every row (the rolling window and the
+    // padding lanes read them unconditionally)
     {
-        const int tail = TileGeom<E>::NP + 5 - n;                  // members n .. NP+4 (padding lanes read them too)
+        const int tail = TileGeom<E>::NP + 5 - n;
         const int per_row = 4 + tail;
         for (int i = threadIdx.x; i < TILE_CT * per_row; i += TILE_THREADS) {
             const int r = i / per_row, k9 = i - r * per_row;
             tile[r * NPS + skew(k9 < 4 ? k9 - 4 : n + k9 - 4)] = 0.0f;
         }
     }
-    // the row numbers are loaded eight at a time (independent global loads), then the copies fire;
-    // they are also left in shared memory for the store pass (rowtab), which then needs no global
-    // index loads at all
+    const bool vec = allow_vec && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src + c0) & 15) == 0) &&
+                     (c0 + TILE_CT <= C);
+    if (vec) {
+        // BATCH row segments per thread are loaded before their shared stores (BATCH = 0: leave the
+        // scheduling of the unrolled loop to the compiler — fewer live registers)
+        constexpr int IT = TileGeom<E>::NP / (TILE_THREADS / 2);
+        const int quad = threadIdx.x & 1;
+        const int64_t cq = c0 + 4 * quad;
+        bool ok0 = true, ok1 = true, ok2 = true, ok3 = true;
+        if (valid) { ok0 = valid[cq]; ok1 = valid[cq + 1]; ok2 = valid[cq + 2]; ok3 = valid[cq + 3]; }
+        float* d0 = tile + (4 * quad) * NPS;
+        const float* col = src + cq;
+        const int j0 = threadIdx.x >> 1;
+        if constexpr (BATCH == 0) {
 #pragma unroll 8
-    for (int j = threadIdx.x / TILE_CT; j < n; j += TILE_THREADS / TILE_CT) {
-        const int32_t row = __ldg(rg + j);
-        if (rowtab && cc == 0) rowtab[j] = row;
-        if (ok) {
-            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst + skew(j));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" :: "r"(saddr), "l"(col + (uint64_t)(uint32_t)row * (uint32_t)ld) : "memory");     // 32x32→64-bit multiply (ld < 2^32 checked by the host)
+            for (int j = j0; j < n; j += TILE_THREADS / 2) {
+                const int32_t row = __ldg(rg + j);
+                if (rowtab && quad == 0) rowtab[j] = row;
+                const float4 x = __ldcs(reinterpret_cast<const float4*>(col + (uint64_t)(uint32_t)row * (uint32_t)ld));
+                const int at = skew(j);
+                d0[at] = ok0 ? x.x : 0.0f;
+                d0[NPS + at] = ok1 ? x.y : 0.0f;
+                d0[2 * NPS + at] = ok2 ? x.z : 0.0f;
+                d0[3 * NPS + at] = ok3 ? x.w : 0.0f;
+            }
         } else {
-            dst[skew(j)] = 0.0f;
+            constexpr int B = BATCH < IT ? BATCH : IT;
+#pragma unroll
+            for (int ib = 0; ib < IT; ib += B) {
+                int32_t row[B];
+                float4 x[B];
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    const int j = j0 + (ib + u) * (TILE_THREADS / 2);
+                    row[u] = (j < n) ? __ldg(rg + j) : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    const int j = j0 + (ib + u) * (TILE_THREADS / 2);
+                    if (j < n) x[u] = __ldcs(reinterpret_cast<const float4*>(col + (uint64_t)(uint32_t)row[u] * (uint32_t)ld));
+                }
+#pragma unroll
+                for (int u = 0; u < B; ++u) {
+                    const int j = j0 + (ib + u) * (TILE_THREADS / 2);
+                    if (j < n) {
+                        if (rowtab && quad == 0) rowtab[j] = row[u];
+                        const int at = skew(j);
+                        d0[at] = ok0 ? x[u].x : 0.0f;
+                        d0[NPS + at] = ok1 ? x[u].y : 0.0f;
+                        d0[2 * NPS + at] = ok2 ? x[u].z : 0.0f;
+                        d0[3 * NPS + at] = ok3 ? x[u].w : 0.0f;
+                    }
+                }
+            }
+        }
+    } else {
+        const int cc = threadIdx.x & (TILE_CT - 1);
+        const int64_t c = c0 + cc;
+        const bool ok = c < C && (!valid || valid[c]);
+        float* dst = tile + cc * NPS;
+        const float* col = src + (ok ? c : 0);
+        constexpr int RS = TILE_THREADS / TILE_CT;       // rows per pass
+        for (int jb = threadIdx.x / TILE_CT; jb < n; jb += 8 * RS) {
+            int32_t row[8];
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) row[u] = (jb + u * RS < n) ? __ldg(rg + jb + u * RS) : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                x[u] = (ok && jb + u * RS < n) ? __ldcs(col + (uint64_t)(uint32_t)row[u] * (uint32_t)ld) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int j = jb + u * RS;
+                if (j < n) {
+                    if (rowtab && cc == 0) rowtab[j] = row[u];
+                    dst[skew(j)] = x[u];
+                }
+            }
         }
     }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-}
-template <int PENDING>
-__device__ __forceinline__ void wait_tile_loads() { asm volatile("cp.async.wait_group %0;\n" :: "n"(PENDING) : "memory"); }
-
-template <int E>
-__device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
-                                          int64_t c0, const int32_t* __restrict__ rg, int n,
-                                          const uint8_t* __restrict__ valid, int32_t* rowtab = nullptr) {
-    issue_tile_load<E>(tile, src, ld, C, c0, rg, n, valid, rowtab);
-    wait_tile_loads<0>();
 }
 
 // ---------------------------------------------------------------- fit
@@ -99,14 +162,14 @@ qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
                    const int32_t* __restrict__ rows, const int32_t* __restrict__ len,
                    const int64_t* __restrict__ off, int max_len,
                    float* __restrict__ state, int64_t state_ld, const uint8_t* __restrict__ valid,
-                   int32_t* __restrict__ nonfinite) {
+                   int32_t* __restrict__ nonfinite, int no_vec) {
     using G = TileGeom<E>;
     extern __shared__ float tile_f[];
     const int g = blockIdx.y;
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
     const int n = len[g];
     const int32_t* rg = rows + (int64_t)g * max_len;
-    load_tile<E>(tile_f, y, ld, C, c0, rg, n, valid);
+    load_tile<E, SDB_FIT_BATCH>(tile_f, y, ld, C, c0, rg, n, valid, !no_vec);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = c0 + warp;
@@ -481,19 +544,50 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
     }
 }
 
-// coalesced store of one output tile (rows of 8 cells)
+// coalesced store of one output tile (rows of 8 cells): 16-byte stores when the rows are aligned
 template <int E>
 __device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictParams& p, int64_t c0,
                                            const int32_t* rowtab, int n) {
     constexpr int NPS = TileGeom<E>::NPS;
-    const int cc = threadIdx.x & (TILE_CT - 1);
-    const int64_t cs = c0 + cc;
-    if (cs < p.C) {
-        float* outp = (float*)p.out + cs;
-        const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
+    float* out = (float*)p.out;
+    const bool vec = !p.no_vec && ((p.ld_out & 3) == 0) && ((reinterpret_cast<uintptr_t>(out + c0) & 15) == 0) &&
+                     (c0 + TILE_CT <= p.C);
+    if (vec) {
+        const int quad = threadIdx.x & 1;
+        const float* s0 = reinterpret_cast<const float*>(tileR) + (4 * quad) * NPS;
+        float* outp = out + c0 + 4 * quad;
+#if SDB_STORE_BATCH
+        constexpr int IT = TileGeom<E>::NP / (TILE_THREADS / 2);
+        const int j0 = threadIdx.x >> 1;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            const int j = j0 + it * (TILE_THREADS / 2);
+            if (j < n) {
+                const int at = skew(j);
+                float4 v4;
+                v4.x = s0[at]; v4.y = s0[NPS + at]; v4.z = s0[2 * NPS + at]; v4.w = s0[3 * NPS + at];
+                __stcs(reinterpret_cast<float4*>(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out), v4);
+            }
+        }
+#else
 #pragma unroll 8
-        for (int j = threadIdx.x / TILE_CT; j < n; j += TILE_THREADS / TILE_CT)
-            __stcs(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out, srcp[skew(j)]);
+        for (int j = threadIdx.x >> 1; j < n; j += TILE_THREADS / 2) {
+            const int at = skew(j);
+            float4 v4;
+            v4.x = s0[at]; v4.y = s0[NPS + at]; v4.z = s0[2 * NPS + at]; v4.w = s0[3 * NPS + at];
+            __stcs(reinterpret_cast<float4*>(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out), v4);
+        }
+#endif
+    } else {
+        const int cc = threadIdx.x & (TILE_CT - 1);
+        const int64_t cs = c0 + cc;
+        if (cs < p.C) {
+            float* outp = out + cs;
+            const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
+#pragma unroll 8
+            for (int j = threadIdx.x / TILE_CT; j < n; j += TILE_THREADS / TILE_CT)
+                __stcs(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out, srcp[skew(j)]);
+        }
     }
 }
 
@@ -525,7 +619,7 @@ qm_predict_tile_kernel(const PredictParams p) {
         // the fitted sorted values are wanted right after the sort: pull the record into L2 now
         if (lane * 32 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(S + lane * 32));
     }
-    load_tile<E>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid, rowtab);
+    load_tile<E, SDB_PRED_BATCH>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid, !p.no_vec, rowtab);
     __syncthreads();
     uint32_t* R = tileR + warp * NPS;
     if (in_range && !active) {
@@ -537,60 +631,6 @@ qm_predict_tile_kernel(const PredictParams p) {
     store_tile<E>(tileR, p, c0, rowtab, n);
 }
 
-// grid = (cell tiles): the CTA walks all groups of its 8 cells; the next group's tile is in flight
-// (cp.async, second input buffer) while the current one is sorted and mapped.
-template <int E, bool SHIFT>
-__global__ void __launch_bounds__(TILE_THREADS, 2)
-qm_predict_tile_pipe_kernel(const PredictParams p) {
-    constexpr int NPS = TileGeom<E>::NPS;
-    extern __shared__ uint32_t smem_u[];
-    float* tileX0 = reinterpret_cast<float*>(smem_u);
-    float* tileX1 = tileX0 + TILE_CT * NPS;
-    uint32_t* tileR = smem_u + 2 * TILE_CT * NPS;
-    int32_t* rowtab0 = reinterpret_cast<int32_t*>(smem_u + 3 * TILE_CT * NPS);
-    int32_t* rowtab1 = rowtab0 + TileGeom<E>::NP;
-    const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t c = c0 + warp;
-    const bool in_range = c < p.C;
-    const bool active = in_range && (!p.valid || p.valid[c]);
-    const int G = p.n_groups;
-    const float* X = (const float*)p.X;
-    issue_tile_load<E>(tileX0, X, p.ld, p.C, c0, p.rows, p.len[0], p.valid, rowtab0);
-    for (int g = 0; g < G; ++g) {
-        float* cur = (g & 1) ? tileX1 : tileX0;
-        float* nxt = (g & 1) ? tileX0 : tileX1;
-        const int n = p.len[g];
-        const int32_t* rg = p.rows + (int64_t)g * p.max_len;
-        const int sg = p.state_gid[g];
-        const int m = p.fit_len[sg];
-        const float* S = (const float*)p.state + (active ? c : 0) * p.state_ld + p.state_off[sg];
-        float xc_f = 0.0f, yc_f = 0.0f;
-        if (active) {
-            if (SHIFT) xc_f = ((const float*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
-            if (p.mode != SDB_MODE_QM && p.return_anoms) yc_f = ((const float*)p.y_climo)[(int64_t)sg * p.ld_climo + c];
-            if (lane * 32 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(S + lane * 32));
-        }
-        if (g + 1 < G) {
-            issue_tile_load<E>(nxt, X, p.ld, p.C, c0, p.rows + (int64_t)(g + 1) * p.max_len, p.len[g + 1], p.valid,
-                               (g & 1) ? rowtab0 : rowtab1);
-            wait_tile_loads<1>();
-        } else {
-            wait_tile_loads<0>();
-        }
-        __syncthreads();                 // tile g has landed; the previous store has finished reading R
-        uint32_t* R = tileR + warp * NPS;
-        if (in_range && !active) {
-            for (int j = lane; j < n; j += 32) R[skew(j)] = __float_as_uint(NAN);
-        } else if (active) {
-            map_cell_group<E, SHIFT>(p, cur + warp * NPS, R, lane, c, n, m, rg, S, (double)xc_f, (double)yc_f);
-        }
-        __syncthreads();
-        store_tile<E>(tileR, p, c0, (g & 1) ? rowtab1 : rowtab0, n);
-        __syncthreads();                 // the row table of group g is rewritten by the load of group g+2
-    }
-}
-
 // ---------------------------------------------------------------- launchers
 template <int E>
 static int launch_fit_tile(const FitParams& f, cudaStream_t st) {
@@ -599,26 +639,18 @@ static int launch_fit_tile(const FitParams& f, cudaStream_t st) {
     if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((f.C + TILE_CT - 1) / TILE_CT), (unsigned)f.n_groups);
     kern<<<grid, TILE_THREADS, smem, st>>>((const float*)f.y, f.ld, f.C, f.rows, f.len, f.off, f.max_len,
-                                           (float*)f.state, f.state_ld, f.valid, f.nonfinite);
+                                           (float*)f.state, f.state_ld, f.valid, f.nonfinite, f.no_vec);
     SDB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 template <int E, bool SHIFT>
-static int launch_predict_tile(const PredictParams& p, cudaStream_t st, bool pipelined) {
-    if (pipelined) {
-        auto kern = qm_predict_tile_pipe_kernel<E, SHIFT>;
-        const size_t smem = (size_t)TILE_CT * 3 * TileGeom<E>::NPS * 4 + 2 * (size_t)TileGeom<E>::NP * 4;
-        if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT));
-        kern<<<grid, TILE_THREADS, smem, st>>>(p);
-    } else {
-        auto kern = qm_predict_tile_kernel<E, SHIFT>;
-        const size_t smem = predict_tile_smem<E>();
-        if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT), (unsigned)p.n_groups);
-        kern<<<grid, TILE_THREADS, smem, st>>>(p);
-    }
+static int launch_predict_tile(const PredictParams& p, cudaStream_t st) {
+    auto kern = qm_predict_tile_kernel<E, SHIFT>;
+    const size_t smem = predict_tile_smem<E>();
+    if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT), (unsigned)p.n_groups);
+    kern<<<grid, TILE_THREADS, smem, st>>>(p);
     SDB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -40,10 +40,10 @@ def eng():
 
 class force_generic:
     """Kernel family selection for a block of code: 'tile' (default float32 tile kernels),
-    'generic' (any dtype / any length kernels), 'pipe' (tile kernels, software-pipelined predict).
+    'generic' (any dtype / any length kernels), 'scalar' (tile kernels without 16-byte row accesses).
     ``True`` / ``False`` are accepted for generic / tile."""
 
-    FLAGS = {'tile': 0, 'generic': 1, 'pipe': 2, True: 1, False: 0}
+    FLAGS = {'tile': 0, 'generic': 1, 'scalar': 2, True: 1, False: 0}
 
     def __init__(self, on=True):
         self.on = on
@@ -154,7 +154,7 @@ def test_bcsd_temperature_golden(dev, golden, name, kw):
     g = golden(name)
     idx_f0 = synth.daily_index(len(g['Xtr']), str(g['start_fit']))
     idx_p0 = synth.daily_index(len(g['Xp']), str(g['start_pred']))
-    with force_generic('pipe'):          # the software-pipelined predict kernel gives the same field
+    with force_generic('scalar'):        # the unaligned-row form of the tile kernels gives the same field
         pw0 = pm().PointWiseDownscaler(pm().BcsdTemperature(**kw))
         pw0.fit(g['Xtr'], g['ytr'], time=idx_f0)
         assert_close(pw0.predict(g['Xp'], time=idx_p0), g['out'], scale=np.nanstd(g['ytr']))
@@ -213,7 +213,7 @@ def test_bcsd_errors(dev):
         pm().BcsdTemperature().fit(pd.DataFrame(np.zeros((10, 1)), index=idx[:10]), pd.DataFrame(np.zeros((10, 1)), index=idx[5:15]))
 
 
-@pytest.mark.parametrize('generic', ['tile', 'generic', 'pipe'])
+@pytest.mark.parametrize('generic', ['tile', 'generic', 'scalar'])
 @pytest.mark.parametrize('anoms', [True, False])
 def test_bcsd_temperature_vs_oracle_ranks(dev, anoms, generic):
     """30-year daily series, ragged cell count, NaN cells; ranks bit-exact, values 1e-5.
@@ -249,7 +249,7 @@ def _bcsd_temperature_vs_oracle_ranks(dev, anoms):
         assert yc[gi, 0] == oracle.bcsd._group_mean_like_pandas(ytr[rows, 0])
 
 
-@pytest.mark.parametrize('family', ['tile', 'pipe'])
+@pytest.mark.parametrize('family', ['tile', 'scalar'])
 @pytest.mark.parametrize('case', ['outlier', 'clusters', 'constant', 'two_values'])
 @pytest.mark.parametrize('model', ['T', 'P'])
 def test_tile_kernel_bucket_fixups(dev, case, model, family):
@@ -300,7 +300,7 @@ def _tile_kernel_bucket_fixups(dev, case, model):
             assert_close(out[:, c], o.astype(np.float32), scale=np.std(ytr[:, c]))
 
 
-@pytest.mark.parametrize('generic', ['tile', 'generic', 'pipe'])
+@pytest.mark.parametrize('generic', ['tile', 'generic', 'scalar'])
 def test_bcsd_precipitation_vs_oracle(dev, generic):
     with force_generic(generic):
         _bcsd_precipitation_vs_oracle(dev)
@@ -490,7 +490,7 @@ def test_random_small_cases_vs_oracle(dev, seed):
         Xtr[:, c] = np.nan
     fit_g = oracle.groups_from_keys(oracle.month_keys(idx_f))
     pred_g = oracle.groups_from_keys(oracle.month_keys(idx_p))
-    for family in ('tile', 'generic', 'pipe'):
+    for family in ('tile', 'generic', 'scalar'):
         with force_generic(family):
             for anoms in (True, False):
                 m = pm().BcsdTemperature(return_anoms=anoms)
