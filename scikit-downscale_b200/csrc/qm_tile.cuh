@@ -41,7 +41,13 @@ template <int E> struct TileGeom {
     // eight rows of a tile start in different banks — conflict-free for every access pattern used
     static constexpr int NPS = (TILE_CT == 8) ? ((E == 32) ? 1092 : 284) : ((E == 32) ? 1096 : 296);
     static constexpr int LOG = (E == 8) ? 8 : 10;
-    static constexpr uint32_t QMAX = (1u << (32 - LOG)) - 1u;   // bucket of the padding items
+    static constexpr uint32_t QMAX = (1u << (32 - LOG)) - 1u;   // largest bucket number
+    // members take buckets 0..QTOP; the padding item at position j takes bucket QTOP + 1 + j, so padding
+    // sorts last in position order and NO two padding items share a bucket (the same-bucket scan after
+    // the sort then needs no "is this a member" guard)
+    static constexpr uint32_t QTOP = QMAX - (uint32_t)NP;
+    static constexpr uint32_t PAD_BASE = (QTOP + 1u) << LOG;    // key of padding position j: PAD_BASE + j * (2^LOG + 1)
+    static constexpr uint32_t PAD_STEP = (1u << LOG) + 1u;
     static_assert(E == 8 || E == 32, "tile kernels are instantiated for NP = 256 and 1024");
 };
 __device__ __forceinline__ int skew(int j) { return j + (j >> 5) + 8; }      // valid for j >= -8
@@ -200,10 +206,11 @@ qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
 // exact-residual FMA correction (Markstein) — three FP64 instructions, no division subroutine.
 static __constant__ double RC_TAB[10] = {0.0, 1.0, 1.0 / 2.0, 1.0 / 3.0, 1.0 / 4.0, 1.0 / 5.0, 1.0 / 6.0, 1.0 / 7.0,
                                          1.0 / 8.0, 1.0 / 9.0};
+static __constant__ double CNT_TAB[10] = {0.0, 1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0, 9.0};
 __device__ __forceinline__ double div_count(double sum, int cnt) {
     const double rc = RC_TAB[cnt];
     const double q0 = sum * rc;
-    const double r = fma(-q0, (double)cnt, sum);
+    const double r = fma(-q0, CNT_TAB[cnt], sum);
     return fma(r, rc, q0);
 }
 
@@ -304,7 +311,7 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
                                                const float* __restrict__ S, double xc, double yc) {
     using G = TileGeom<E>;
     constexpr int LOG = G::LOG;
-    constexpr uint32_t QMAX = G::QMAX;
+    constexpr uint32_t QTOP = G::QTOP;
     constexpr uint32_t IDX = (1u << LOG) - 1u;
     const int j0 = lane * E;
     const int j1 = (j0 + E < n) ? j0 + E : n;
@@ -349,41 +356,46 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
         // ---- 2. exact rank keys → monotone bucket number, packed with the member position.
         // The bounds are a guess (value range + 1/8 margin); keys outside clamp to the end
         // buckets, which keeps the map monotone — whatever shares a bucket is compared exactly.
+        // Every position is computed unconditionally (the padding members are zeros and their slots of
+        // R exist); only the final key is a select between the member's packed word and the padding key.
+        const uint32_t pad0 = G::PAD_BASE + (uint32_t)j0 * G::PAD_STEP;
         if (SHIFT) {
             const double range = (double)hi32 - (double)lo32;
             const double lo = (double)lo32 - 0.125 * range, hi = (double)hi32 + 0.125 * range;
-            const double scale = (hi > lo && isfinite(hi - lo)) ? (double)(QMAX - 1) / (hi - lo) : 0.0;
+            const double scale = (hi > lo && isfinite(hi - lo)) ? (double)QTOP / (hi - lo) : 0.0;
+            const double nls = -lo * scale;                 // t = key * scale - lo * scale: one monotone FMA
+            // members of the window that exist: 9 - a - b, a = 4 - j (front, lane 0 only), b = j + 5 - n (back)
+            const int back0 = j0 + 5 - n;                   // b of e = 0
+            const bool front = (lane == 0);
             double sum = 0.0;
 #pragma unroll
             for (int i = 0; i < 9; ++i) sum += (double)xh[i];
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                if (e < nj) {
-                    const double shift = div_count(sum, win_count(j0 + e, n)) - xc;
-                    const double t = (((double)xh[e + 4] - shift) - lo) * scale;
-                    uint32_t q = (t > 0.0) ? __double2uint_rd(t) : 0u;           // also maps NaN to 0
-                    q = q > QMAX - 1 ? QMAX - 1 : q;
-                    v[e].k = (q << LOG) | (uint32_t)(j0 + e);
-                    R[rb + e] = __float_as_uint((float)(shift - park_off));
-                } else {
-                    v[e].k = 0xffffffffu;
-                }
+                int b = back0 + e;
+                b = b < 0 ? 0 : (b > 8 ? 8 : b);            // clamp: padding positions still index the tables
+                int cnt = 9 - b;
+                if (e < 4) { cnt -= front ? (4 - e) : 0; cnt = cnt < 1 ? 1 : cnt; }
+                const double shift = div_count(sum, cnt) - xc;
+                const double t = fma((double)xh[e + 4] - shift, scale, nls);
+                uint32_t q = __double2uint_rd(t);           // saturating: negative and NaN map to 0
+                q = q > QTOP ? QTOP : q;
+                const uint32_t w = (q << LOG) + (uint32_t)(j0 + e);
+                v[e].k = (e < nj) ? w : pad0 + (uint32_t)e * G::PAD_STEP;
+                R[rb + e] = __float_as_uint((float)(shift - park_off));
                 sum += (double)xh[e + 9];
                 sum -= (double)xh[e];
             }
         } else {
             const float range = hi32 - lo32;
-            const float scale = (range > 0.0f && isfinite(range)) ? (float)(QMAX - 1) / range : 0.0f;
+            const float scale = (range > 0.0f && isfinite(range)) ? (float)QTOP / range : 0.0f;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                if (e < nj) {
-                    const float t = (xh[e] - lo32) * scale;
-                    uint32_t q = (t > 0.0f) ? __float2uint_rd(t) : 0u;
-                    q = q > QMAX - 1 ? QMAX - 1 : q;
-                    v[e].k = (q << LOG) | (uint32_t)(j0 + e);
-                } else {
-                    v[e].k = 0xffffffffu;
-                }
+                const float t = (xh[e] - lo32) * scale;
+                uint32_t q = __float2uint_rd(t);            // saturating: negative and NaN map to 0
+                q = q > QTOP ? QTOP : q;
+                const uint32_t w = (q << LOG) + (uint32_t)(j0 + e);
+                v[e].k = (e < nj) ? w : pad0 + (uint32_t)e * G::PAD_STEP;
             }
         }
     }
@@ -395,8 +407,9 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const uint32_t kn = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-        bm_eq |= ((e + 1 < nj) && (((v[e].k ^ kn) >> LOG) == 0u)) ? (1u << e) : 0u;
+        bm_eq |= (((v[e].k ^ kn) >> LOG) == 0u) ? (1u << e) : 0u;       // padding never shares a bucket
     }
+    if (lane == 31) bm_eq &= 0x7fffffffu >> (32 - E);      // the last position has no successor (nxt_first is the lane's own)
     __syncwarp();                             // shifts parked in R are visible to every lane
 
     // ---- 4. (member, rank) of every sorted position → mapped value → output
@@ -464,8 +477,7 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
         }
         if (mode == 0) {
 #pragma unroll
-            for (int e = 0; e < E; ++e)
-                if (e < nj) finish((int)(v[e].k & IDX), sv[e]);
+            for (int e = 0; e < E; ++e) finish((int)(v[e].k & IDX), sv[e]);    // padding positions land in slots >= n of R
         } else {
             // same scatter with the isolated same-bucket pairs patched: an inverted pair exchanges its
             // members, an exactly tied pair both take the higher order statistic (tie-max rank)
@@ -473,12 +485,10 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
             const uint32_t prv_last_k = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                if (e < nj) {
-                    uint32_t w = v[e].k;
-                    if ((bm_gt >> e) & 1u) w = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
-                    else if ((e == 0) ? prev_gt : ((bm_gt >> (e == 0 ? 0 : e - 1)) & 1u)) w = (e == 0) ? prv_last_k : v[e == 0 ? e : e - 1].k;
-                    finish((int)(w & IDX), ((bm_tie >> e) & 1u) ? sv[e + 1] : sv[e]);
-                }
+                uint32_t w = v[e].k;
+                if ((bm_gt >> e) & 1u) w = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
+                else if ((e == 0) ? prev_gt : ((bm_gt >> (e == 0 ? 0 : e - 1)) & 1u)) w = (e == 0) ? prv_last_k : v[e == 0 ? e : e - 1].k;
+                finish((int)(w & IDX), ((bm_tie >> e) & 1u) ? sv[e + 1] : sv[e]);
             }
         }
     } else if (mode == 3) {

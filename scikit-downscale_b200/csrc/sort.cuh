@@ -15,6 +15,7 @@
 // a group's prediction values (quantile.py:138,488) — see qm_kernels.cu.
 #pragma once
 #include <cstdint>
+#include <type_traits>
 
 namespace sdb {
 
@@ -61,6 +62,21 @@ __device__ __forceinline__ I item_shfl_xor(const I& v, int mask) {
     return o;
 }
 
+// Pipe balancing (SDB_HYBRID bit mask, experiment builds): VIMNMX runs on the ALU pipe only (one warp
+// instruction per 2 cycles per scheduler), which is what bounds the sorting network.  The "hybrid"
+// compare-exchange takes min on the ALU pipe and max = a + b - min as two IMADs on the FMA pipe (exact
+// modulo 2^32).  The multipliers come from constant memory so that ptxas cannot fold the IMADs back
+// into IADD3 / VIMNMX.  bit 0: thread-local sort, bit 1: thread-local merge, bit 2: cross-lane keep.
+#ifndef SDB_HYBRID
+#define SDB_HYBRID 2
+#endif
+static __constant__ uint32_t SDB_MULS[4] = {1u, 0xffffffffu, 0xfffffffeu, 0u};   // 1, -1, -2
+__device__ __forceinline__ void cmpswap_hybrid(K32& a, K32& b) {
+    const uint32_t lo = min(a.k, b.k);
+    const uint32_t t = a.k * SDB_MULS[0] + b.k;
+    b.k = lo * SDB_MULS[1] + t;
+    a.k = lo;
+}
 // ascending compare-exchange inside one thread
 __device__ __forceinline__ void cmpswap(K32& a, K32& b) {
     uint32_t lo = min(a.k, b.k), hi = max(a.k, b.k);
@@ -76,7 +92,12 @@ __device__ __forceinline__ void cmpswap(I& a, I& b) {
 __device__ __forceinline__ K32 keep(const K32& v, const K32& o, bool lower) {
     K32 r;
     r.k = min(v.k, o.k);                 // min, then a predicated max over it: two VIMNMX, no select
+#if SDB_HYBRID & 4
+    const uint32_t d = r.k * SDB_MULS[2] + (v.k * SDB_MULS[0] + o.k);      // max - min
+    r.k = d * (lower ? 0u : 1u) + r.k;
+#else
     if (!lower) r.k = max(v.k, o.k);
+#endif
     return r;
 }
 template <class I>
@@ -93,7 +114,11 @@ __device__ __forceinline__ I keep(const I& v, const I& o, bool lower) {
 template <class I, int E>
 __device__ __forceinline__ void local_sort(I (&v)[E]) {
     static_assert(E == 8 || E == 16 || E == 32, "sorting networks are generated for 8, 16 and 32 items");
+#if SDB_HYBRID & 1
+#define SDB_CE(a, b) if constexpr (std::is_same<I, K32>::value) cmpswap_hybrid((K32&)v[a], (K32&)v[b]); else cmpswap(v[a], v[b]);
+#else
 #define SDB_CE(a, b) cmpswap(v[a], v[b]);
+#endif
     if constexpr (E == 8) { SDB_SORT_NET_8 }
     else if constexpr (E == 16) { SDB_SORT_NET_16 }
     else { SDB_SORT_NET_32 }
@@ -107,6 +132,9 @@ __device__ __forceinline__ void local_merge(I (&v)[E]) {
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             int p = e ^ j;
+#if SDB_HYBRID & 2
+            if constexpr (std::is_same<I, K32>::value) { if (p > e) cmpswap_hybrid((K32&)v[e], (K32&)v[p]); } else
+#endif
             if (p > e) cmpswap(v[e], v[p]);
         }
     }
@@ -152,6 +180,27 @@ __device__ __forceinline__ void cross_stage(I (&v)[E], int tid, int tmask, bool 
 template <class I, int E, int NT>
 __device__ __forceinline__ void sort_blocked(I (&v)[E], int tid, uint32_t* xchg) {
     local_sort<I, E>(v);
+#ifndef SDB_SORT_UNROLL
+#define SDB_SORT_UNROLL 0
+#endif
+    if constexpr (SDB_SORT_UNROLL != 0 && NT == 32 && item_words<I>::value == 1) {
+        // keys-only warp sort: merge levels unrolled (no register shuffling at loop back-edges)
+#pragma unroll
+        for (int kt = 2; kt <= NT; kt <<= 1) {
+            cross_stage<I, E, NT, true>(v, tid, kt - 1, (tid & (kt >> 1)) == 0, xchg);
+            if constexpr (SDB_SORT_UNROLL == 1) {
+#pragma unroll
+                for (int jt = kt >> 2; jt > 0; jt >>= 1)
+                    cross_stage<I, E, NT, false>(v, tid, jt, (tid & jt) == 0, xchg);
+            } else {
+#pragma unroll 1
+                for (int jt = kt >> 2; jt > 0; jt >>= 1)
+                    cross_stage<I, E, NT, false>(v, tid, jt, (tid & jt) == 0, xchg);
+            }
+            local_merge<I, E>(v);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int kt = 2; kt <= NT; kt <<= 1) {          // kt = k / E : merge level in units of threads
         cross_stage<I, E, NT, true>(v, tid, kt - 1, (tid & (kt >> 1)) == 0, xchg);
