@@ -71,7 +71,16 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
     static_assert(TILE_CT == 8, "the vector path assumes 8-cell tiles");
     // zeros around the group: members -4..-1 and n..NP+4 of every row (the rolling window and the
     // padding lanes read them unconditionally)
-    {
+    const bool vec = allow_vec && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src + c0) & 15) == 0) &&
+                     (c0 + TILE_CT <= C);
+    if (vec && BATCH != 0) {
+        // the vector path below writes every position 0..NP-1 itself (zeros from n on): only the 4 + 5
+        // halo slots outside [0, NP) are left
+        if (threadIdx.x < TILE_CT * 9) {
+            const int r = threadIdx.x / 9, k9 = threadIdx.x - r * 9;
+            tile[r * NPS + skew(k9 < 4 ? k9 - 4 : TileGeom<E>::NP + k9 - 4)] = 0.0f;
+        }
+    } else {
         const int tail = TileGeom<E>::NP + 5 - n;
         const int per_row = 4 + tail;
         for (int i = threadIdx.x; i < TILE_CT * per_row; i += TILE_THREADS) {
@@ -79,8 +88,6 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
             tile[r * NPS + skew(k9 < 4 ? k9 - 4 : n + k9 - 4)] = 0.0f;
         }
     }
-    const bool vec = allow_vec && ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src + c0) & 15) == 0) &&
-                     (c0 + TILE_CT <= C);
     if (vec) {
         // BATCH row segments per thread are loaded before their shared stores (BATCH = 0: leave the
         // scheduling of the unrolled loop to the compiler — fewer live registers)
@@ -118,19 +125,20 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
 #pragma unroll
                 for (int u = 0; u < B; ++u) {
                     const int j = j0 + (ib + u) * (TILE_THREADS / 2);
+                    x[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     if (j < n) x[u] = __ldcs(reinterpret_cast<const float4*>(col + (uint64_t)(uint32_t)row[u] * (uint32_t)ld));
                 }
 #pragma unroll
                 for (int u = 0; u < B; ++u) {
+                    // every position is stored (zeros from n on), no branch: the rows behind the group are
+                    // the zero padding the rolling window and the padding lanes read
                     const int j = j0 + (ib + u) * (TILE_THREADS / 2);
-                    if (j < n) {
-                        if (rowtab && quad == 0) rowtab[j] = row[u];
-                        const int at = skew(j);
-                        d0[at] = ok0 ? x[u].x : 0.0f;
-                        d0[NPS + at] = ok1 ? x[u].y : 0.0f;
-                        d0[2 * NPS + at] = ok2 ? x[u].z : 0.0f;
-                        d0[3 * NPS + at] = ok3 ? x[u].w : 0.0f;
-                    }
+                    if (rowtab && quad == 0) rowtab[j] = row[u];
+                    const int at = skew(j);
+                    d0[at] = ok0 ? x[u].x : 0.0f;
+                    d0[NPS + at] = ok1 ? x[u].y : 0.0f;
+                    d0[2 * NPS + at] = ok2 ? x[u].z : 0.0f;
+                    d0[3 * NPS + at] = ok3 ? x[u].w : 0.0f;
                 }
             }
         }
@@ -308,7 +316,7 @@ static __device__ __noinline__ float mapped_value_general(const float* __restric
 template <int E, bool SHIFT>
 __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* myX, uint32_t* R, int lane,
                                                int64_t c, int n, int m, const int32_t* __restrict__ rg,
-                                               const float* __restrict__ S, double xc, double yc) {
+                                               const float* __restrict__ S, bool quad_ok, double xc, double yc) {
     using G = TileGeom<E>;
     constexpr int LOG = G::LOG;
     constexpr uint32_t QTOP = G::QTOP;
@@ -343,12 +351,23 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
             const int addr = (E == 32) ? rb + e + (e < 0 ? -1 : (e >= 32 ? 1 : 0)) : skew(jj);
             xh[i] = myX[addr];                              // zeros outside [0, n) by construction of the tile
         }
-        float lo32 = INFINITY, hi32 = -INFINITY, nanacc = 0.0f;
+        // The bucket bounds are only a guess (whatever falls outside clamps to the end buckets and is
+        // compared exactly), so they come from the lanes whose block is full: no per-member guard.  The
+        // one partially filled lane joins only when no lane is full (groups shorter than E).
+        float lo32 = xh[HL], hi32 = xh[HL], nanacc = 0.0f;
 #pragma unroll
         for (int e = 0; e < E; ++e) {
             const float x = xh[e + HL];
-            if (e < nj) { lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x); }
+            if (e > 0) { lo32 = fminf(lo32, x); hi32 = fmaxf(hi32, x); }
             nanacc = fmaf(x, 0.0f, nanacc);                 // NaN / inf anywhere → NaN (padding members are zeros)
+        }
+        if (nj < E) {
+            lo32 = INFINITY; hi32 = -INFINITY;
+            if (n < E) {                                    // warp-uniform: a group inside lane 0
+#pragma unroll
+                for (int e = 0; e < E; ++e)
+                    if (e < nj) { lo32 = fminf(lo32, xh[e + HL]); hi32 = fmaxf(hi32, xh[e + HL]); }
+            }
         }
         if (nanacc != nanacc && p.nonfinite) atomicOr(p.nonfinite, 1);
         lo32 = warp_min(lo32); hi32 = warp_max(hi32);
@@ -458,22 +477,20 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
         const bool adjacent = ((bm_tie & (bm_tie >> 1)) != 0) || ((lane < 31) && ((bm_tie >> (E - 1)) & 1u) && nxt_tie0);
         pairs_only = !__any_sync(0xffffffffu, adjacent);
     }
-    if ((mode == 0 || pairs_only) && same && !p.rank_out && (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(S) & 15) == 0)) {
+    if ((mode == 0 || pairs_only) && same && !p.rank_out && (E % 4 == 0) && quad_ok) {
         // the common case: same length and (almost) one member per bucket — the member at sorted
         // position pos takes the fitted order statistic S[pos]; the lane's 32 values are 8 vector loads
         float sv[E + 1];
 #pragma unroll
+        // quads past the group's last one re-read that last quad (positions >= n only feed padding slots);
+        // the last quad may reach up to 3 values into the 16-byte alignment gap behind the group, which
+        // belongs to the cell's record
+        const int last4 = (n - 1) & ~3;
+#pragma unroll
         for (int q4 = 0; q4 < E / 4; ++q4) {
             const int pos = j0 + 4 * q4;
-            if (pos + 3 < n) {
-                const float4 t4 = __ldg(reinterpret_cast<const float4*>(S + pos));
-                sv[4 * q4] = t4.x; sv[4 * q4 + 1] = t4.y; sv[4 * q4 + 2] = t4.z; sv[4 * q4 + 3] = t4.w;
-            } else {
-                sv[4 * q4] = pos < n ? __ldg(S + pos) : 0.0f;
-                sv[4 * q4 + 1] = pos + 1 < n ? __ldg(S + pos + 1) : 0.0f;
-                sv[4 * q4 + 2] = pos + 2 < n ? __ldg(S + pos + 2) : 0.0f;
-                sv[4 * q4 + 3] = 0.0f;
-            }
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(S + (pos < last4 ? pos : last4)));
+            sv[4 * q4] = t4.x; sv[4 * q4 + 1] = t4.y; sv[4 * q4 + 2] = t4.z; sv[4 * q4 + 3] = t4.w;
         }
         if (mode == 0) {
 #pragma unroll
@@ -602,9 +619,12 @@ __device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictP
 }
 
 // grid = (cell tiles, groups): one (tile, group) per CTA
+#ifndef SDB_PRED_CTAS
+#define SDB_PRED_CTAS (24 / TILE_CT)
+#endif
 template <int E, bool SHIFT>
-__global__ void __launch_bounds__(TILE_THREADS, 24 / TILE_CT)
-qm_predict_tile_kernel(const PredictParams p) {
+__global__ void __launch_bounds__(TILE_THREADS, SDB_PRED_CTAS)
+qm_predict_tile_kernel(const PredictParams p) {   // SDB_PRED_CTAS: experiment builds
     constexpr int NPS = TileGeom<E>::NPS;
     extern __shared__ uint32_t smem_u[];
     float* tileX = reinterpret_cast<float*>(smem_u);                        // inputs of the group
@@ -621,7 +641,10 @@ qm_predict_tile_kernel(const PredictParams p) {
     // per-(cell, group) scalars: fetched before the tile load so their latency hides behind it
     const int sg = p.state_gid[g];
     const int m = p.fit_len[sg];
-    const float* S = (const float*)p.state + (active ? c : 0) * p.state_ld + p.state_off[sg];
+    const int64_t soff = p.state_off[sg];
+    const float* S = (const float*)p.state + (active ? c : 0) * p.state_ld + soff;
+    // 16-byte loads of the fitted values: aligned, and the group's last quad stays inside the cell's record
+    const bool quad_ok = ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && (soff + (((m - 1) & ~3) + 4) <= p.state_ld);
     float xc_f = 0.0f, yc_f = 0.0f;
     if (active) {
         if (SHIFT) xc_f = ((const float*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
@@ -635,7 +658,7 @@ qm_predict_tile_kernel(const PredictParams p) {
     if (in_range && !active) {
         for (int j = lane; j < n; j += 32) R[skew(j)] = __float_as_uint(NAN);
     } else if (active) {
-        map_cell_group<E, SHIFT>(p, tileX + warp * NPS, R, lane, c, n, m, rg, S, (double)xc_f, (double)yc_f);
+        map_cell_group<E, SHIFT>(p, tileX + warp * NPS, R, lane, c, n, m, rg, S, quad_ok, (double)xc_f, (double)yc_f);
     }
     __syncthreads();
     store_tile<E>(tileR, p, c0, rowtab, n);

@@ -91,6 +91,15 @@ __device__ __forceinline__ void cmpswap(I& a, I& b) {
 // keep the smaller (lower==true) or the larger of own item v and partner item o
 __device__ __forceinline__ K32 keep(const K32& v, const K32& o, bool lower) {
     K32 r;
+#if !(SDB_HYBRID & 4) && !defined(SDB_KEEP_PLAIN)
+    // two complementary predicated VIMNMX writing the SAME register: the result replaces v in place, so
+    // the runtime stage loops carry no register copies (the "min, then predicated max over it" form
+    // needs a temporary and costs one MOV per item per stage)
+    r.k = v.k;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p min.u32 %0, %0, %1;\n\t@!p max.u32 %0, %0, %1;\n\t}"
+        : "+r"(r.k) : "r"(o.k), "r"((int)lower));
+    return r;
+#endif
     r.k = min(v.k, o.k);                 // min, then a predicated max over it: two VIMNMX, no select
 #if SDB_HYBRID & 4
     const uint32_t d = r.k * SDB_MULS[2] + (v.k * SDB_MULS[0] + o.k);      // max - min
