@@ -65,6 +65,25 @@ extern "C" {
 #define SDB_ANALOG_MEAN   3
 #define SDB_ANALOG_REGRESSION 4   /* AnalogRegression._predict_one_step  gard.py:191-224 */
 
+/* CunnaneTransformer settings of the quantile map (quantile.py:420-432, reached through
+ * QuantileMapper(qt_kwargs=...) / BcsdBase(qm_kwargs={'qt_kwargs': ...})).  `extrapolate`: which tails of the
+ * fitted CDF continue as the OLS line through the n_endpoints end points (quantile.py:526-543); the
+ * other tails clamp to the end value like np.interp.  None and '1to1' both mean SDB_EXTRAPOLATE_NONE
+ * (CunnaneTransformer treats them alike).  A NULL pointer = the defaults {0.4, 0.4, 10, BOTH}. */
+#define SDB_EXTRAPOLATE_NONE 0
+#define SDB_EXTRAPOLATE_MIN  1
+#define SDB_EXTRAPOLATE_MAX  2
+#define SDB_EXTRAPOLATE_BOTH 3
+typedef struct sdb_cunnane_opts {
+    double alpha;         /* plotting positions (i - alpha) / (n + 1 - alpha - beta)   quantile.py:23-43.
+                           * NOTE: the reference's CunnaneTransformer never hands its alpha / beta to
+                           * plotting_positions (quantile.py:462), i.e. it always maps with 0.4 / 0.4; a
+                           * drop-in caller passes 0.4 here whatever the user asked for. */
+    double beta;
+    int32_t n_endpoints;  /* >= 1 */
+    int32_t extrapolate;  /* SDB_EXTRAPOLATE_* */
+} sdb_cunnane_opts;
+
 #define SDB_MAX_GROUP_LEN 16384   /* longest group (padded to a power of two) one CTA sorts */
 #define SDB_MAX_ANALOGS   256
 
@@ -127,6 +146,7 @@ int sdb_qm_fit(const void* y, int dtype, int64_t ld, int64_t n_cells,
  * mode, bcsd.py:48-49); otherwise device int32[T_pred * 9] with the row numbers of the
  * window members of every row (-1 = absent) — the general case where the climate-trend
  * grouping differs from the mapping groups ('daily_nasa-nex', bcsd.py:53,250,275).
+ * cunnane: HOST pointer to the CunnaneTransformer settings, NULL = defaults.
  * rank_out: optional device int32 [T_pred, ld_out] receiving the 1-based in-group rank
  * (parity instrumentation), or NULL.  out_dtype may differ from dtype (the reference's
  * estimators return float64, its wrapper casts to X.dtype — core.py:129).
@@ -137,7 +157,7 @@ int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, int64_t n_cel
                    const int32_t* fit_len, const int64_t* state_off, int max_fit_len,
                    const void* sorted_state, int64_t state_ld,
                    const void* x_climo, const void* y_climo, int64_t ld_climo,
-                   int return_anoms, const int32_t* roll_nbr,
+                   int return_anoms, const int32_t* roll_nbr, const sdb_cunnane_opts* cunnane,
                    void* out, int out_dtype, int64_t ld_out, int32_t* rank_out,
                    const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
 
@@ -150,14 +170,20 @@ int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, int64_t n_cel
  *   out     [T_q, 3, C] (out_dtype): pred, exceedance_prob, prediction_error
  *   knn_idx optional device int32 [T_q, k, C] (parity instrumentation) or NULL
  *   rand_idx device int32 [T_q, C], only for SDB_ANALOG_SAMPLE (host-drawn, gard.py:315)
- *   has_thresh/thresh: PureAnalog threshold masking (gard.py:303-308, 338-343)
+ *   has_thresh/thresh: PureAnalog threshold masking (gard.py:303-308, 338-343); for
+ *           SDB_ANALOG_REGRESSION the exceedance split of gard.py:201-215: exceedance_prob =
+ *           P(class 0) of an L2-regularised logistic regression (inverse strength logistic_c,
+ *           sklearn's C, default 1.0; solved to machine precision where the reference's lbfgs
+ *           stops at tol 1e-4) and the least-squares fit restricted to the analogs above thresh.
+ *           A query whose analogs are ALL at or below thresh makes the reference raise
+ *           ("needs samples of at least 2 classes"): the kernel ORs 2 into *nonfinite.
  * Replaces  AnalogBase.fit + PureAnalog.predict / AnalogRegression.predict
  *           gard.py:58-87, 152-224, 273-364.
  */
 int sdb_analog_predict(int kind, const void* X_train, const void* y_train, const void* X_query,
                        int dtype, int64_t ld, int64_t n_cells,
                        int t_fit, int t_query, int n_features, int k,
-                       int has_thresh, double thresh, const int32_t* rand_idx,
+                       int has_thresh, double thresh, double logistic_c, const int32_t* rand_idx,
                        void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
                        const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
 

@@ -73,7 +73,7 @@ def bcsd_temperature_fit(X: np.ndarray, y: np.ndarray, fit_groups, mean_how: str
 
 
 def bcsd_temperature_predict(st: dict, X: np.ndarray, roll_groups, qm_groups,
-                             return_anoms: bool = True, return_rank: bool = False):
+                             return_anoms: bool = True, return_rank: bool = False, qt: dict | None = None):
     """BcsdTemperature.predict (bcsd.py:230-281).
 
     ``roll_groups``: groups of ``climate_trend`` (bcsd.py:250); ``qm_groups``: groups
@@ -94,7 +94,7 @@ def bcsd_temperature_predict(st: dict, X: np.ndarray, roll_groups, qm_groups,
     ranks = np.empty(T, dtype=np.int64)
     for key, rows in qm_groups:                                      # bcsd.py:260, 69-79
         xqm[rows], ranks[rows] = quantile_mapper_transform(no_shift[rows], st['sorted'][key],
-                                                           return_rank=True)
+                                                           return_rank=True, **(qt or {}))
     out = shift + xqm                                                # bcsd.py:263
     if return_anoms:                                                 # bcsd.py:266-267
         for key, rows in qm_groups:
@@ -117,14 +117,14 @@ def bcsd_precipitation_fit(y: np.ndarray, fit_groups, return_anoms: bool = True,
 
 
 def bcsd_precipitation_predict(st: dict, X: np.ndarray, qm_groups, return_anoms: bool = True,
-                               return_rank: bool = False):
+                               return_rank: bool = False, qt: dict | None = None):
     """BcsdPrecipitation.predict (bcsd.py:149-185): QM per group, then ratio anomalies."""
     X = np.asarray(X).reshape(-1)
     out = np.empty(len(X), dtype=np.float64)
     ranks = np.empty(len(X), dtype=np.int64)
     for key, rows in qm_groups:                                      # bcsd.py:167
         out[rows], ranks[rows] = quantile_mapper_transform(X[rows], st['sorted'][key],
-                                                           return_rank=True)
+                                                           return_rank=True, **(qt or {}))
     if return_anoms:                                                 # bcsd.py:170-185
         for key, rows in qm_groups:
             out[rows] = out[rows] / np.float64(st['y_climo'][key])

@@ -2,7 +2,7 @@
 
 Follows skdownscale/pointwise_models/gard.py:58-87 (AnalogBase.fit),
 :273-364 (PureAnalog.predict) and :152-224 (AnalogRegression.predict /
-_predict_one_step, thresh=None).  The neighbour search of
+_predict_one_step, with and without ``thresh``).  The neighbour search of
 sklearn.neighbors.KDTree (scikit-learn, pinned 1.7.2 in the reference's
 uv.lock:3033-3034; not vendored) is restated as an exact float64 brute force:
 squared Euclidean distance accumulated feature by feature, neighbours in
@@ -90,29 +90,79 @@ def pure_analog_predict(X_train, y_train, X_query, n_analogs: int = 200, kind: s
     return (out, inds, dist) if return_inds else out
 
 
-def analog_regression_predict(X_train, y_train, X_query, n_analogs: int = 200, thresh=None,
-                              return_inds: bool = False):
-    """AnalogRegression.fit + predict with thresh=None (gard.py:152-224).
+def logistic_fit_exact(x: np.ndarray, b: np.ndarray, C: float = 1.0):
+    """The optimum sklearn's ``LogisticRegression(C=C)`` (l2 penalty, intercept not penalised,
+    lbfgs) iterates towards (gard.py:172,209):  minimise
+    ``sum_i log(1 + exp(-s_i (w.x_i + c))) + ||w||^2 / (2 C)``, ``s_i = +-1``.
+    scikit-learn (pinned 1.7.2, uv.lock:3033-3034; not vendored) stops lbfgs at a projected
+    gradient of ``tol = 1e-4`` on the per-sample-averaged objective, so its answer is this optimum
+    only to ~1e-4..1e-3; here damped Newton runs to machine precision.  Returns (w, c)."""
+    x = np.asarray(x, dtype=np.float64)
+    t = np.asarray(b, dtype=np.float64)
+    n, p = x.shape
+    Z = np.hstack([x, np.ones((n, 1))])
+    th = np.zeros(p + 1)
+    reg = np.r_[np.full(p, 1.0 / C), 0.0]
 
-    Per timestep: k nearest analogs → ordinary least squares with intercept on
-    the float64 analog predictors (sklearn LinearRegression = centred
-    ``lstsq``, minimum-norm when rank deficient) → prediction at the query
-    point, exceedance_prob = 1.0, prediction_error = in-sample RMSE."""
-    if thresh is not None:
-        raise NotImplementedError('AnalogRegression(thresh=...) needs the logistic step (SURVEY §8f row 4)')
+    def objective(v):
+        z = Z @ v
+        return np.sum(np.logaddexp(0.0, z) - t * z) + 0.5 * np.sum(reg * v * v)
+
+    f = objective(th)
+    for _ in range(200):
+        z = Z @ th
+        mu = 1.0 / (1.0 + np.exp(-z))
+        g = Z.T @ (mu - t) + reg * th
+        H = (Z * (mu * (1.0 - mu))[:, None]).T @ Z + np.diag(reg)
+        d = np.linalg.solve(H + 1e-300 * np.eye(p + 1), -g)
+        step = 1.0
+        while True:
+            cand = th + step * d
+            fc = objective(cand)
+            if fc <= f + 1e-4 * step * (g @ d) or step < 1e-10:
+                break
+            step *= 0.5
+        th, f_old, f = cand, f, fc
+        if np.max(np.abs(step * d)) < 1e-14 * max(1.0, np.max(np.abs(th))):
+            break
+    return th[:p], th[p]
+
+
+def analog_regression_predict(X_train, y_train, X_query, n_analogs: int = 200, thresh=None,
+                              return_inds: bool = False, logistic_C: float = 1.0):
+    """AnalogRegression.fit + predict (gard.py:152-224).
+
+    Per timestep: k nearest analogs → [thresh] logistic regression of ``y > thresh`` on the
+    analog predictors, ``exceedance_prob = predict_proba[0, 0]`` = P(class 0) (gard.py:201-212; 1.0
+    when every analog exceeds; ValueError when none does, like sklearn) → ordinary least squares
+    with intercept on the (exceeding) float64 analog predictors (sklearn LinearRegression = centred
+    ``lstsq``, minimum-norm when rank deficient) → prediction at the query point,
+    prediction_error = in-sample RMSE."""
     A = np.asarray(X_train, dtype=np.float64)
     if A.ndim == 1:
         A = A[:, None]
     Q = np.asarray(X_query)
     if Q.ndim == 1:
         Q = Q[:, None]
-    y_ = np.asarray(y_train).reshape(-1)
-    k_ = min(n_analogs, len(y_))
+    y_raw = np.asarray(y_train).reshape(-1)
+    k_ = min(n_analogs, len(y_raw))
     _, inds = knn_bruteforce(A, Q, k_)                              # gard.py:194
     out = np.empty((Q.shape[0], 3), dtype=np.float64)
     for i in range(Q.shape[0]):
         x = A[inds[i]]                                              # gard.py:197
-        y = y_[inds[i]].astype(np.float64)                          # gard.py:198 (+ sklearn cast)
+        yk = y_raw[inds[i]]                                         # gard.py:198
+        prob = 1.0
+        if thresh is not None:
+            exceed = yk > thresh                                    # gard.py:201-202 (in y's dtype)
+            if not exceed.all():                                    # gard.py:208-212
+                if not exceed.any():
+                    raise ValueError('This solver needs samples of at least 2 classes in the data, but the data '
+                                     'contains only one class: 0')
+                w, c0 = logistic_fit_exact(x, exceed, logistic_C)
+                z = float(Q[i].astype(np.float64) @ w + c0)
+                prob = 1.0 - 1.0 / (1.0 + np.exp(-z))               # predict_proba[0, 0] = P(class 0)
+            x, yk = x[exceed], yk[exceed]
+        y = yk.astype(np.float64)                                   # sklearn casts the target
         xo = x.mean(axis=0)
         yo = y.mean()
         coef, *_ = np.linalg.lstsq(x - xo, y - yo, rcond=None)      # gard.py:215
@@ -120,5 +170,5 @@ def analog_regression_predict(X_train, y_train, X_query, n_analogs: int = 200, t
         y_hat = x @ coef + intercept                                # gard.py:218
         err = np.sqrt(np.mean((y - y_hat) ** 2))                    # gard.py:219
         pred = Q[i].astype(np.float64) @ coef + intercept           # gard.py:221
-        out[i] = (pred, 1.0, err)                                   # gard.py:224
+        out[i] = (pred, prob, err)                                  # gard.py:224
     return (out, inds) if return_inds else out

@@ -45,16 +45,24 @@ def _ols_line(x: np.ndarray, y: np.ndarray) -> tuple[float, float]:
     return float(slope), float(ym - slope * xm)
 
 
-def cunnane_inverse(q: np.ndarray, sorted_fit: np.ndarray, n_endpoints: int = 10) -> np.ndarray:
-    """CunnaneTransformer.inverse_transform (quantile.py:523-545), extrapolate='both'.
+def cunnane_inverse(q: np.ndarray, sorted_fit: np.ndarray, n_endpoints: int = 10, alpha: float = 0.4,
+                    beta: float = 0.4, extrapolate='both') -> np.ndarray:
+    """CunnaneTransformer.inverse_transform (quantile.py:523-545).
 
     ``q`` float64 quantiles, ``sorted_fit`` the fitted sorted values.  Interior:
     ``np.interp(q, pp_fit, vals_fit)``; outside ``[pp_fit[0], pp_fit[-1]]``: OLS
-    line through the first / last ``n_endpoints`` (pp, val) pairs.
+    line through the first / last ``n_endpoints`` (pp, val) pairs on the tails
+    ``extrapolate`` names ('min', 'max', 'both'), np.interp's end-value clamp on the others
+    (None and '1to1' clamp both, quantile.py:526-527).
     """
     q = np.asarray(q, dtype=np.float64)
+    # quantile.py:462: ``Cdf(plotting_positions(len(X)), np.sort(X))`` — the constructor's alpha / beta
+    # are never handed to plotting_positions, so the reference always uses 0.4 / 0.4 (replicated)
+    del alpha, beta
     pp = plotting_positions(len(sorted_fit))
-    vals = np.interp(q, pp, sorted_fit, left=-np.inf, right=np.inf)
+    left = -np.inf if extrapolate in ('min', 'both') else None
+    right = np.inf if extrapolate in ('max', 'both') else None
+    vals = np.interp(q, pp, sorted_fit, left=left, right=right)
     if np.isinf(vals).any():
         lower = np.nonzero(-np.inf == vals)[0]
         upper = np.nonzero(np.inf == vals)[0]
@@ -70,14 +78,16 @@ def cunnane_inverse(q: np.ndarray, sorted_fit: np.ndarray, n_endpoints: int = 10
 
 
 def quantile_mapper_transform(x: np.ndarray, sorted_fit: np.ndarray, n_endpoints: int = 10,
-                              return_rank: bool = False):
+                              return_rank: bool = False, alpha: float = 0.4, beta: float = 0.4,
+                              extrapolate='both'):
     """QuantileMapper.transform (quantile.py:109-147, detrend=False).
 
     ``x`` is ranked against ITSELF (quantile.py:138), the resulting quantiles are
     pushed through the fitted inverse CDF (quantile.py:139).  Returns float64.
+    The keyword arguments are the ``qt_kwargs`` of the reference (CunnaneTransformer settings).
     """
     x = np.asarray(x).reshape(-1)
     r = rank_max_ties(x)
-    q = plotting_positions(len(x))[r - 1]
-    out = cunnane_inverse(q, sorted_fit, n_endpoints=n_endpoints)
+    q = plotting_positions(len(x))[r - 1]                # alpha / beta are ignored by the reference (quantile.py:462)
+    out = cunnane_inverse(q, sorted_fit, n_endpoints=n_endpoints, alpha=alpha, beta=beta, extrapolate=extrapolate)
     return (out, r) if return_rank else out

@@ -59,13 +59,14 @@ def pointwise_fit_predict(spec: dict, X_train, y_train, X_pred, index_fit=None, 
             continue
         if name == 'QuantileMapper':
             st = quantile.quantile_mapper_fit(np.asarray(y_train)[:, c])
-            res = quantile.quantile_mapper_transform(X_pred[:, c], st)
+            res = quantile.quantile_mapper_transform(X_pred[:, c], st, **(spec.get('qt_kwargs') or {}))
         elif name == 'BcsdTemperature':
             st = bcsd.bcsd_temperature_fit(np.asarray(X_train)[:, c], np.asarray(y_train)[:, c], fit_groups, how)
-            res = bcsd.bcsd_temperature_predict(st, X_pred[:, c], roll_groups, qm_groups, anoms)
+            res = bcsd.bcsd_temperature_predict(st, X_pred[:, c], roll_groups, qm_groups, anoms,
+                                                qt=spec.get('qt_kwargs'))
         elif name == 'BcsdPrecipitation':
             st = bcsd.bcsd_precipitation_fit(np.asarray(y_train)[:, c], fit_groups, anoms, how)
-            res = bcsd.bcsd_precipitation_predict(st, X_pred[:, c], qm_groups, anoms)
+            res = bcsd.bcsd_precipitation_predict(st, X_pred[:, c], qm_groups, anoms, qt=spec.get('qt_kwargs'))
         elif name == 'PureAnalog':
             res = gard.pure_analog_predict(np.asarray(X_train)[:, :, c], np.asarray(y_train)[:, c],
                                            X_pred[:, :, c], spec.get('n_analogs', 200),
@@ -74,7 +75,7 @@ def pointwise_fit_predict(spec: dict, X_train, y_train, X_pred, index_fit=None, 
         elif name == 'AnalogRegression':
             res = gard.analog_regression_predict(np.asarray(X_train)[:, :, c], np.asarray(y_train)[:, c],
                                                  X_pred[:, :, c], spec.get('n_analogs', 200),
-                                                 spec.get('thresh'))
+                                                 spec.get('thresh'), logistic_C=spec.get('logistic_C', 1.0))
         else:
             raise ValueError(name)
         if multi:

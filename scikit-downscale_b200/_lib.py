@@ -16,6 +16,14 @@ LIB_PATH = os.environ.get('SDB_LIBRARY') or os.path.join(_HERE, 'csrc', 'libsdb.
 SDB_F32, SDB_F64 = 0, 1
 MODE_QM, MODE_BCSD_P, MODE_BCSD_T = 0, 1, 2
 MEAN_GROUPBY, MEAN_FRAME = 0, 1
+EXTRAPOLATE = {None: 0, '1to1': 0, 'min': 1, 'max': 2, 'both': 3}    # SDB_EXTRAPOLATE_* (include/sdb.h)
+
+
+class CunnaneOpts(ctypes.Structure):
+    """``sdb_cunnane_opts`` of include/sdb.h: CunnaneTransformer settings (quantile.py:420-432)."""
+    _fields_ = [('alpha', c_double), ('beta', c_double), ('n_endpoints', ctypes.c_int32), ('extrapolate', ctypes.c_int32)]
+
+
 ANALOG_BEST, ANALOG_SAMPLE, ANALOG_WEIGHT, ANALOG_MEAN, ANALOG_REGRESSION = 0, 1, 2, 3, 4
 
 # every symbol include/sdb.h declares: (restype, argtypes)
@@ -34,13 +42,13 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_int,
                                c_void_p, c_int64,
                                c_void_p, c_void_p, c_int64,
-                               c_int, c_void_p,
+                               c_int, c_void_p, c_void_p,
                                c_void_p, c_int, c_int64, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
     'sdb_analog_predict': (c_int, [c_int, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int64, c_int64,
                                    c_int, c_int, c_int, c_int,
-                                   c_int, c_double, c_void_p,
+                                   c_int, c_double, c_double, c_void_p,
                                    c_void_p, c_int, c_int64, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
 }

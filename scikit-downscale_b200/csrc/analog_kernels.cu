@@ -3,7 +3,7 @@
 // Replaces, per cell and per query timestep,
 //   AnalogBase.fit (KDTree build)                  skdownscale/pointwise_models/gard.py:58-87
 //   PureAnalog.predict                              gard.py:273-364
-//   AnalogRegression.predict / _predict_one_step    gard.py:152-224 (thresh=None)
+//   AnalogRegression.predict / _predict_one_step    gard.py:152-224 (with and without thresh)
 // and the Python loop over cells around them (core.py:69-143).
 //
 // The k-nearest-neighbour search is an EXACT float64 brute force: squared Euclidean
@@ -37,7 +37,7 @@ constexpr int AN_PMAX = 8;          // generic-feature kernel handles up to this
 struct AnalogParams {
     const void* Xtr; const void* ytr; const void* Xq;
     int64_t ld; int64_t C; int t_fit, t_query, p, k, kind;
-    int has_thresh; double thresh; const int32_t* rand_idx;
+    int has_thresh; double thresh; double logistic_c; const int32_t* rand_idx;
     void* out; int out_f64; int64_t ld_out; int32_t* knn_idx;
     const uint8_t* valid; int32_t* nonfinite;
 };
@@ -95,26 +95,225 @@ __device__ void pure_analog_epilogue(const AnalogParams& a, int q, int64_t c, in
     store3(a, q, c, pred, prob, err);
 }
 
+// Minimum-norm solution of the symmetric positive semi-definite p x p system A beta = b
+// (A given by its lower triangle) through a cyclic Jacobi eigen-decomposition: what
+// scipy.linalg.lstsq (gelsd) under sklearn's LinearRegression returns when the centred analog
+// cloud is rank deficient (fewer regression samples than predictors + 1).
+template <int P>
+__device__ void sym_minnorm_solve(const double (&A)[P][P], const double (&b)[P], int p, double (&beta)[P]) {
+    double M[P][P], V[P][P];
+#pragma unroll
+    for (int f = 0; f < P; ++f)
+#pragma unroll
+        for (int g = 0; g < P; ++g) {
+            M[f][g] = (f < p && g < p) ? (g <= f ? A[f][g] : A[g][f]) : 0.0;
+            V[f][g] = (f == g) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, diag = 0.0;
+#pragma unroll
+        for (int f = 0; f < P; ++f) {
+            diag += M[f][f] * M[f][f];
+#pragma unroll
+            for (int g = 0; g < f; ++g) off += M[f][g] * M[f][g];
+        }
+        if (!(off > 1e-60 * diag) || !(off > 0.0)) break;
+#pragma unroll
+        for (int f = 1; f < P; ++f) {
+#pragma unroll
+            for (int g = 0; g < f; ++g) {
+                const double apq = M[f][g];
+                if (apq == 0.0) continue;
+                const double theta = (M[g][g] - M[f][f]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                // rotate rows / columns f and g
+#pragma unroll
+                for (int h = 0; h < P; ++h) {
+                    const double mhf = M[h][f], mhg = M[h][g];
+                    M[h][f] = cs * mhf - sn * mhg;
+                    M[h][g] = sn * mhf + cs * mhg;
+                }
+#pragma unroll
+                for (int h = 0; h < P; ++h) {
+                    const double mfh = M[f][h], mgh = M[g][h];
+                    M[f][h] = cs * mfh - sn * mgh;
+                    M[g][h] = sn * mfh + cs * mgh;
+                }
+#pragma unroll
+                for (int h = 0; h < P; ++h) {
+                    const double vhf = V[h][f], vhg = V[h][g];
+                    V[h][f] = cs * vhf - sn * vhg;
+                    V[h][g] = sn * vhf + cs * vhg;
+                }
+            }
+        }
+    }
+    double lmax = 0.0;
+#pragma unroll
+    for (int f = 0; f < P; ++f) lmax = fmax(lmax, M[f][f]);
+#pragma unroll
+    for (int f = 0; f < P; ++f) beta[f] = 0.0;
+#pragma unroll
+    for (int e = 0; e < P; ++e) {
+        const double lam = M[e][e];
+        if (e < p && lam > 1e-13 * lmax && lam > 0.0) {
+            double vb = 0.0;
+#pragma unroll
+            for (int f = 0; f < P; ++f) vb += V[f][e] * b[f];
+            vb /= lam;
+#pragma unroll
+            for (int f = 0; f < P; ++f) beta[f] += V[f][e] * vb;
+        }
+    }
+}
+
+// L2-regularised logistic regression of the exceedance flags on the k analog predictors, solved to
+// machine precision by damped Newton (sklearn's LogisticRegression(C) minimises the same objective
+// with lbfgs stopped at tol = 1e-4, so it agrees with this optimum to ~1e-4): returns
+// predict_proba(X)[0, 0] = P(class 0) at the query point.  gard.py:205-212
+template <int P, typename XF, typename EF>
+__device__ double logistic_prob_class0(int k, int p, const XF& xv, const EF& exceeds, const double (&xq)[P], double Creg) {
+    constexpr int D = P + 1;
+    double th[D];
+#pragma unroll
+    for (int f = 0; f < D; ++f) th[f] = 0.0;
+    const double lam = 1.0 / Creg;
+    auto objective = [&](const double (&v)[D]) -> double {
+        double s = 0.0;
+        for (int i = 0; i < k; ++i) {
+            double z = v[P];
+#pragma unroll
+            for (int f = 0; f < P; ++f) if (f < p) z += v[f] * xv(i, f);
+            s += fmax(z, 0.0) + log1p(exp(-fabs(z))) - (exceeds(i) ? z : 0.0);
+        }
+        double r = 0.0;
+#pragma unroll
+        for (int f = 0; f < P; ++f) if (f < p) r += v[f] * v[f];
+        return s + 0.5 * lam * r;
+    };
+    double fcur = objective(th);
+    for (int it = 0; it < 100; ++it) {
+        double g[D], H[D][D];
+#pragma unroll
+        for (int f = 0; f < D; ++f) { g[f] = 0.0;
+#pragma unroll
+            for (int h = 0; h < D; ++h) H[f][h] = 0.0; }
+        for (int i = 0; i < k; ++i) {
+            double xi[D];
+#pragma unroll
+            for (int f = 0; f < P; ++f) xi[f] = (f < p) ? xv(i, f) : 0.0;
+            xi[P] = 1.0;
+            double z = 0.0;
+#pragma unroll
+            for (int f = 0; f < D; ++f) z += th[f] * xi[f];
+            const double mu = 1.0 / (1.0 + exp(-z));
+            const double r = mu - (exceeds(i) ? 1.0 : 0.0), w = mu * (1.0 - mu);
+#pragma unroll
+            for (int f = 0; f < D; ++f) { g[f] += r * xi[f];
+#pragma unroll
+                for (int h = 0; h <= f; ++h) H[f][h] += w * xi[f] * xi[h]; }
+        }
+#pragma unroll
+        for (int f = 0; f < P; ++f) {
+            if (f < p) { g[f] += lam * th[f]; H[f][f] += lam; }
+            else H[f][f] = 1.0;                              // unused predictor slots: identity, zero step
+        }
+        // Cholesky of H (positive definite: ridge on the weights, both classes present for the intercept)
+        bool ok = true;
+#pragma unroll
+        for (int f = 0; f < D; ++f) {
+#pragma unroll
+            for (int h = 0; h <= f; ++h) {
+                double sacc = H[f][h];
+#pragma unroll
+                for (int u = 0; u < h; ++u) sacc -= H[f][u] * H[h][u];
+                if (h == f) { if (!(sacc > 0.0)) { ok = false; sacc = 1.0; } H[f][f] = sqrt(sacc); }
+                else H[f][h] = sacc / H[h][h];
+            }
+        }
+        double d[D];
+#pragma unroll
+        for (int f = 0; f < D; ++f) {
+            double sacc = -g[f];
+#pragma unroll
+            for (int u = 0; u < f; ++u) sacc -= H[f][u] * d[u];
+            d[f] = sacc / H[f][f];
+        }
+#pragma unroll
+        for (int f = D - 1; f >= 0; --f) {
+            double sacc = d[f];
+#pragma unroll
+            for (int u = f + 1; u < D; ++u) sacc -= H[u][f] * d[u];
+            d[f] = sacc / H[f][f];
+        }
+        if (!ok) {                                           // numerically flat curvature: plain gradient step
+#pragma unroll
+            for (int f = 0; f < D; ++f) d[f] = -g[f];
+        }
+        double gd = 0.0;
+#pragma unroll
+        for (int f = 0; f < D; ++f) gd += g[f] * d[f];
+        double step = 1.0, fnew = fcur;
+        double cand[D];
+        for (;;) {                                           // Armijo backtracking
+#pragma unroll
+            for (int f = 0; f < D; ++f) cand[f] = th[f] + step * d[f];
+            fnew = objective(cand);
+            if (fnew <= fcur + 1e-4 * step * gd || step < 1e-10) break;
+            step *= 0.5;
+        }
+        double dmax = 0.0, tmax = 1.0;
+#pragma unroll
+        for (int f = 0; f < D; ++f) { dmax = fmax(dmax, fabs(step * d[f])); th[f] = cand[f]; tmax = fmax(tmax, fabs(cand[f])); }
+        fcur = fnew;
+        if (dmax < 1e-14 * tmax) break;
+    }
+    double z = th[P];
+#pragma unroll
+    for (int f = 0; f < P; ++f) if (f < p) z += th[f] * xq[f];
+    return 1.0 - 1.0 / (1.0 + exp(-z));
+}
+
 // Ordinary least squares with intercept on the k analogs (sklearn LinearRegression:
-// centred least squares), prediction at the query point, in-sample RMSE.  gard.py:215-221
-template <typename T, int P, typename IdxF>
+// centred least squares, minimum norm when rank deficient), prediction at the query point,
+// in-sample RMSE.  With a threshold: exceedance probability from the logistic fit above and the
+// regression restricted to the analogs above the threshold.  gard.py:191-224
+template <typename T, int P, bool LOGIT, typename IdxF>
 __device__ void regression_epilogue(const AnalogParams& a, int q, int64_t c, int k, const IdxF& idx, const double (&xq)[P]) {
     const T* X = (const T*)a.Xtr;
     const T* y = (const T*)a.ytr;
     const int p = (P == AN_PMAX) ? a.p : P;
     auto xv = [&](int i, int f) -> double { return (double)X[((int64_t)idx(i) * a.p + f) * a.ld + c]; };
     auto yv = [&](int i) -> double { return (double)y[(int64_t)idx(i) * a.ld + c]; };
+    const T th = (T)a.thresh;
+    // LOGIT (compile time) = a threshold was given: the plain regression keeps its register budget
+    auto use = [&](int i) -> bool { return !LOGIT || (y[(int64_t)idx(i) * a.ld + c] > th); };   // gard.py:201-204
+    int m = k;
+    double prob = 1.0;
+    if constexpr (LOGIT) {
+        m = 0;
+        for (int i = 0; i < k; ++i) m += use(i) ? 1 : 0;
+        if (m == 0) {
+            // no analog above the threshold: sklearn's LogisticRegression raises (one class only) — bit 1
+            if (a.nonfinite) atomicOr(a.nonfinite, 2);
+            store3(a, q, c, NAN, NAN, NAN);
+            return;
+        }
+        if (m < k) prob = logistic_prob_class0<P>(k, p, xv, use, xq, a.logistic_c);
+    }
     double xm[P], ym = 0.0;
 #pragma unroll
     for (int f = 0; f < P; ++f) xm[f] = 0.0;
     for (int i = 0; i < k; ++i) {
+        if (!use(i)) continue;
         ym += yv(i);
 #pragma unroll
         for (int f = 0; f < P; ++f) if (f < p) xm[f] += xv(i, f);
     }
-    ym /= (double)k;
+    ym /= (double)m;
 #pragma unroll
-    for (int f = 0; f < P; ++f) xm[f] /= (double)k;
+    for (int f = 0; f < P; ++f) xm[f] /= (double)m;
     // normal equations of the centred problem: A (p x p, symmetric) beta = b
     double A[P][P], b[P];
 #pragma unroll
@@ -122,6 +321,7 @@ __device__ void regression_epilogue(const AnalogParams& a, int q, int64_t c, int
 #pragma unroll
         for (int g = 0; g < P; ++g) A[f][g] = 0.0; }
     for (int i = 0; i < k; ++i) {
+        if (!use(i)) continue;
         double dx[P];
 #pragma unroll
         for (int f = 0; f < P; ++f) dx[f] = (f < p) ? xv(i, f) - xm[f] : 0.0;
@@ -131,45 +331,54 @@ __device__ void regression_epilogue(const AnalogParams& a, int q, int64_t c, int
 #pragma unroll
             for (int g = 0; g <= f; ++g) A[f][g] += dx[f] * dx[g]; }
     }
-    // Cholesky A = L L^T (lower, in place); a zero pivot (degenerate analog cloud) drops that
-    // direction, i.e. a minimum-norm-like solution with beta_f = 0.
     double beta[P];
-    bool live[P];
+    bool solved = false;
+    if constexpr (LOGIT) {
+        // few analogs above the threshold: rank-deficient centred cloud → the minimum-norm solution
+        // (only compiled into the threshold kernels; without a threshold m = k > p in practice)
+        if (m <= p) { sym_minnorm_solve<P>(A, b, p, beta); solved = true; }
+    }
+    if (!solved) {
+        // Cholesky A = L L^T (lower, in place); a zero pivot (degenerate analog cloud) drops that
+        // direction, i.e. a minimum-norm-like solution with beta_f = 0.
+        bool live[P];
 #pragma unroll
-    for (int f = 0; f < P; ++f) {
-        live[f] = f < p;
+        for (int f = 0; f < P; ++f) {
+            live[f] = f < p;
 #pragma unroll
-        for (int g = 0; g <= f; ++g) {
-            double s = A[f][g];
+            for (int g = 0; g <= f; ++g) {
+                double s = A[f][g];
 #pragma unroll
-            for (int h = 0; h < g; ++h) s -= A[f][h] * A[g][h];
-            if (g == f) {
-                if (!(s > 1e-300) || !live[f]) { live[f] = false; A[f][f] = 1.0; }
-                else A[f][f] = sqrt(s);
-            } else {
-                A[f][g] = live[g] ? s / A[g][g] : 0.0;
+                for (int h = 0; h < g; ++h) s -= A[f][h] * A[g][h];
+                if (g == f) {
+                    if (!(s > 1e-300) || !live[f]) { live[f] = false; A[f][f] = 1.0; }
+                    else A[f][f] = sqrt(s);
+                } else {
+                    A[f][g] = live[g] ? s / A[g][g] : 0.0;
+                }
             }
         }
-    }
 #pragma unroll
-    for (int f = 0; f < P; ++f) {                      // forward substitution
-        double s = b[f];
+        for (int f = 0; f < P; ++f) {                      // forward substitution
+            double s = b[f];
 #pragma unroll
-        for (int h = 0; h < f; ++h) s -= A[f][h] * beta[h];
-        beta[f] = live[f] ? s / A[f][f] : 0.0;
-    }
+            for (int h = 0; h < f; ++h) s -= A[f][h] * beta[h];
+            beta[f] = live[f] ? s / A[f][f] : 0.0;
+        }
 #pragma unroll
-    for (int f = P - 1; f >= 0; --f) {                 // back substitution
-        double s = beta[f];
+        for (int f = P - 1; f >= 0; --f) {                 // back substitution
+            double s = beta[f];
 #pragma unroll
-        for (int h = f + 1; h < P; ++h) s -= A[h][f] * beta[h];
-        beta[f] = live[f] ? s / A[f][f] : 0.0;
+            for (int h = f + 1; h < P; ++h) s -= A[h][f] * beta[h];
+            beta[f] = live[f] ? s / A[f][f] : 0.0;
+        }
     }
     double icpt = ym;
 #pragma unroll
     for (int f = 0; f < P; ++f) icpt -= xm[f] * beta[f];
     double sse = 0.0;
     for (int i = 0; i < k; ++i) {
+        if (!use(i)) continue;
         double yh = icpt;
 #pragma unroll
         for (int f = 0; f < P; ++f) if (f < p) yh += xv(i, f) * beta[f];
@@ -179,11 +388,11 @@ __device__ void regression_epilogue(const AnalogParams& a, int q, int64_t c, int
     double pred = icpt;
 #pragma unroll
     for (int f = 0; f < P; ++f) if (f < p) pred += xq[f] * beta[f];
-    store3(a, q, c, pred, 1.0, sqrt(sse / (double)k));
+    store3(a, q, c, pred, prob, sqrt(sse / (double)m));
 }
 
 // ---- the search kernel
-template <typename T, int P, int KREG>
+template <typename T, int P, int KREG, bool LOGIT>
 __global__ void __launch_bounds__(AN_THREADS)
 analog_kernel(const AnalogParams a) {
     constexpr int AN_CHUNK = AnChunk<P>::value;
@@ -415,7 +624,7 @@ analog_kernel(const AnalogParams a) {
         double xq[P];
 #pragma unroll
         for (int f = 0; f < P; ++f) xq[f] = xqv(f);
-        if (a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<T, P>(a, q, c, k, idx, xq);
+        if (LOGIT || a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<T, P, LOGIT>(a, q, c, k, idx, xq);
         else pure_analog_epilogue<T>(a, q, c, k, idx, dist2);
     } else {
         auto idx = [&](int i) -> int { return bi[i]; };
@@ -423,7 +632,7 @@ analog_kernel(const AnalogParams a) {
         double xq[P];
 #pragma unroll
         for (int f = 0; f < P; ++f) xq[f] = xqv(f);
-        if (a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<T, P>(a, q, c, k, idx, xq);
+        if (LOGIT || a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<T, P, LOGIT>(a, q, c, k, idx, xq);
         else pure_analog_epilogue<T>(a, q, c, k, idx, dist2);
     }
 }
@@ -433,8 +642,14 @@ static int launch_analog(const AnalogParams& a, cudaStream_t st) {
     const int64_t n_tiles = (a.t_query + AN_THREADS - 1) / AN_THREADS;
     if (n_tiles * a.C > 2147483647LL) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_analog_predict: too many (cell, query tile) pairs for one launch; split the shard");
     dim3 grid((unsigned)(n_tiles * a.C));
-    if (a.k <= AN_KREG) analog_kernel<T, P, AN_KREG><<<grid, AN_THREADS, 0, st>>>(a);
-    else                analog_kernel<T, P, 0><<<grid, AN_THREADS, 0, st>>>(a);
+    const bool logit = (a.kind == SDB_ANALOG_REGRESSION) && a.has_thresh;
+    if (a.k <= AN_KREG) {
+        if (logit) analog_kernel<T, P, AN_KREG, true><<<grid, AN_THREADS, 0, st>>>(a);
+        else       analog_kernel<T, P, AN_KREG, false><<<grid, AN_THREADS, 0, st>>>(a);
+    } else {
+        if (logit) analog_kernel<T, P, 0, true><<<grid, AN_THREADS, 0, st>>>(a);
+        else       analog_kernel<T, P, 0, false><<<grid, AN_THREADS, 0, st>>>(a);
+    }
     SDB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -457,7 +672,7 @@ using namespace sdb;
 extern "C" int sdb_analog_predict(int kind, const void* X_train, const void* y_train, const void* X_query,
                                   int dtype, int64_t ld, int64_t n_cells,
                                   int t_fit, int t_query, int n_features, int k,
-                                  int has_thresh, double thresh, const int32_t* rand_idx,
+                                  int has_thresh, double thresh, double logistic_c, const int32_t* rand_idx,
                                   void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
                                   const uint8_t* cell_valid, int32_t* nonfinite, void* stream) {
     if (!X_train || !y_train || !X_query || !out) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: NULL pointer");
@@ -467,13 +682,13 @@ extern "C" int sdb_analog_predict(int kind, const void* X_train, const void* y_t
     if (k < 1 || k > SDB_MAX_ANALOGS || k > t_fit) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: k=%d out of range (1..min(%d, T_fit))", k, SDB_MAX_ANALOGS);
     if (kind < SDB_ANALOG_BEST || kind > SDB_ANALOG_REGRESSION) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: unknown kind %d", kind);
     if (kind == SDB_ANALOG_SAMPLE && !rand_idx) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: sample_analogs needs rand_idx");
-    if (kind == SDB_ANALOG_REGRESSION && has_thresh) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_analog_predict: AnalogRegression(thresh=...) is not implemented");
+    if (kind == SDB_ANALOG_REGRESSION && has_thresh && !(logistic_c > 0.0)) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: logistic_c must be positive");
     if ((dtype != SDB_F32 && dtype != SDB_F64) || (out_dtype != SDB_F32 && out_dtype != SDB_F64))
         return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: bad dtype");
     AnalogParams a;
     a.Xtr = X_train; a.ytr = y_train; a.Xq = X_query; a.ld = ld; a.C = n_cells;
     a.t_fit = t_fit; a.t_query = t_query; a.p = n_features; a.k = k; a.kind = kind;
-    a.has_thresh = has_thresh; a.thresh = thresh; a.rand_idx = rand_idx;
+    a.has_thresh = has_thresh; a.thresh = thresh; a.logistic_c = logistic_c; a.rand_idx = rand_idx;
     a.out = out; a.out_f64 = (out_dtype == SDB_F64); a.ld_out = ld_out; a.knn_idx = knn_idx;
     a.valid = cell_valid; a.nonfinite = nonfinite;
     cudaStream_t st = (cudaStream_t)stream;

@@ -115,7 +115,7 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
                               const int32_t* fit_len, const int64_t* state_off, int max_fit_len,
                               const void* sorted_state, int64_t state_ld,
                               const void* x_climo, const void* y_climo, int64_t ld_climo,
-                              int return_anoms, const int32_t* roll_nbr,
+                              int return_anoms, const int32_t* roll_nbr, const sdb_cunnane_opts* cunnane,
                               void* out, int out_dtype, int64_t ld_out, int32_t* rank_out,
                               const uint8_t* cell_valid, int32_t* nonfinite, void* stream) {
     if (!X || !rows || !len || !state_gid || !fit_len || !state_off || !sorted_state || !out)
@@ -137,6 +137,15 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
     p.roll_nbr = roll_nbr; p.out = out; p.ld_out = ld_out; p.rank_out = rank_out; p.valid = cell_valid; p.nonfinite = nonfinite;
     p.mode = mode; p.out_f64 = (out_dtype == SDB_F64); p.n_groups = n_groups;
     p.no_vec = (g_debug_flags & 2) != 0;
+    p.alpha = 0.4; p.beta = 0.4; p.n_endpoints = 10; p.extrap_lo = 1; p.extrap_hi = 1;   // quantile.py:420-432 defaults
+    if (cunnane) {
+        if (cunnane->n_endpoints < 1) return sdb_fail(SDB_E_INVALID, "sdb_qm_predict: n_endpoints must be >= 1");
+        if (cunnane->extrapolate < SDB_EXTRAPOLATE_NONE || cunnane->extrapolate > SDB_EXTRAPOLATE_BOTH)
+            return sdb_fail(SDB_E_INVALID, "sdb_qm_predict: unknown extrapolate code %d", cunnane->extrapolate);
+        p.alpha = cunnane->alpha; p.beta = cunnane->beta; p.n_endpoints = cunnane->n_endpoints;
+        p.extrap_lo = (cunnane->extrapolate & SDB_EXTRAPOLATE_MIN) != 0;
+        p.extrap_hi = (cunnane->extrapolate & SDB_EXTRAPOLATE_MAX) != 0;
+    }
     const int kind = (mode != SDB_MODE_BCSD_T) ? KIND_RAW : (roll_nbr ? KIND_SHIFT_TAB : KIND_SHIFT);
     cudaStream_t st = (cudaStream_t)stream;
     const int longest = max_len > max_fit_len ? max_len : max_fit_len;

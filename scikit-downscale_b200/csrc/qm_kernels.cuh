@@ -118,6 +118,10 @@ struct PredictParams {
     int out_f64;     // output element type: 0 float, 1 double
     int n_groups;
     int no_vec;      // testing: tile kernels use the 4-byte (unaligned-safe) row loads and stores
+    // CunnaneTransformer settings (quantile.py:420-432): plotting-position parameters, number of tail
+    // points of the OLS extrapolation, and which tails extrapolate (otherwise np.interp clamps)
+    double alpha, beta;
+    int n_endpoints, extrap_lo, extrap_hi;
 };
 
 // kernel flavours (compile-time): what the rank keys are
@@ -131,20 +135,24 @@ __device__ __forceinline__ void store_out(void* out, int out_f64, int64_t at, do
 
 // Cunnane plotting position pp_len(i), i 1-based, exactly as numpy evaluates
 // (np.arange(1, n+1) - 0.4) / (n + 1.0 - 0.4 - 0.4)        quantile.py:43
-__device__ __forceinline__ double pp_denominator(int len) { return (((double)len + 1.0) - 0.4) - 0.4; }
-__device__ __forceinline__ double pp_of(int i, double den) { return ((double)i - 0.4) / den; }
+struct Cunnane { double alpha, beta; int ne; bool lo, hi; };
+__device__ __forceinline__ Cunnane cunnane_of(const PredictParams& p) {
+    return Cunnane{p.alpha, p.beta, p.n_endpoints, p.extrap_lo != 0, p.extrap_hi != 0};
+}
+__device__ __forceinline__ double pp_denominator(int len, const Cunnane& cu) { return (((double)len + 1.0) - cu.alpha) - cu.beta; }
+__device__ __forceinline__ double pp_of(int i, double den, const Cunnane& cu) { return ((double)i - cu.alpha) / den; }
 
 // OLS line through `ne` (pp, value) points starting at 1-based index i0 (quantile.py:532-543;
 // sklearn LinearRegression = centred least squares; slope 0 when the abscissae coincide,
 // which is the minimum-norm lstsq answer for a single point).  S(i): 0-based sorted value.
 template <class Acc>
-__device__ void ols_tail(const Acc& S, int i0, int ne, double den, double& slope, double& icpt) {
+__device__ void ols_tail(const Acc& S, int i0, int ne, double den, const Cunnane& cu, double& slope, double& icpt) {
     double xm = 0.0, ym = 0.0;
-    for (int k = 0; k < ne; ++k) { xm += pp_of(i0 + k, den); ym += S(i0 - 1 + k); }
+    for (int k = 0; k < ne; ++k) { xm += pp_of(i0 + k, den, cu); ym += S(i0 - 1 + k); }
     xm /= (double)ne; ym /= (double)ne;
     double sxy = 0.0, sxx = 0.0;
     for (int k = 0; k < ne; ++k) {
-        double dx = pp_of(i0 + k, den) - xm;
+        double dx = pp_of(i0 + k, den, cu) - xm;
         sxy += dx * (S(i0 - 1 + k) - ym);
         sxx += dx * dx;
     }
@@ -156,29 +164,35 @@ __device__ void ols_tail(const Acc& S, int i0, int ne, double den, double& slope
 // quantile of rank r of n (CunnaneTransformer.inverse_transform, quantile.py:523-545 =
 // np.interp + OLS tails)
 template <class Acc>
-__device__ double inverse_cdf_acc(int r, int n, int m, const Acc& S, double dn, double dm) {
+__device__ double inverse_cdf_acc(int r, int n, int m, const Acc& S, double dn, double dm, const Cunnane& cu) {
     if (n == m) return S(r - 1);                     // q lands exactly on knot r: np.interp returns fp[r-1]
-    const double q = pp_of(r, dn);
-    const double p1 = pp_of(1, dm), pm = pp_of(m, dm);
-    const int ne = m < 10 ? m : 10;
-    if (q < p1) { double a, b; ols_tail(S, 1, ne, dm, a, b); return a * q + b; }
-    if (q > pm) { double a, b; ols_tail(S, m - ne + 1, ne, dm, a, b); return a * q + b; }
+    const double q = pp_of(r, dn, cu);
+    const double p1 = pp_of(1, dm, cu), pm = pp_of(m, dm, cu);
+    const int ne = m < cu.ne ? m : cu.ne;
+    if (q < p1) {                                    // left=-inf + OLS tail, or np.interp's default clamp
+        if (!cu.lo) return S(0);
+        double a, b; ols_tail(S, 1, ne, dm, cu, a, b); return a * q + b;
+    }
+    if (q > pm) {
+        if (!cu.hi) return S(m - 1);
+        double a, b; ols_tail(S, m - ne + 1, ne, dm, cu, a, b); return a * q + b;
+    }
     if (q == pm || m == 1) return S(m - 1);
-    int j = (int)floor(q * dm + 0.4);
+    int j = (int)floor(q * dm + cu.alpha);
     j = j < 1 ? 1 : (j > m - 1 ? m - 1 : j);
-    while (j > 1 && pp_of(j, dm) > q) --j;
-    while (j < m - 1 && pp_of(j + 1, dm) <= q) ++j;
-    const double xj = pp_of(j, dm);
+    while (j > 1 && pp_of(j, dm, cu) > q) --j;
+    while (j < m - 1 && pp_of(j + 1, dm, cu) <= q) ++j;
+    const double xj = pp_of(j, dm, cu);
     if (q == xj) return S(j - 1);
     const double yj = S(j - 1), yj1 = S(j);
-    const double slope = (yj1 - yj) / (pp_of(j + 1, dm) - xj);
+    const double slope = (yj1 - yj) / (pp_of(j + 1, dm, cu) - xj);
     return slope * (q - xj) + yj;
 }
 
 template <typename T>
-__device__ double inverse_cdf(int r, int n, int m, const T* __restrict__ S, double dn, double dm) {
+__device__ double inverse_cdf(int r, int n, int m, const T* __restrict__ S, double dn, double dm, const Cunnane& cu) {
     auto acc = [&](int i) -> double { return (double)S[i]; };
-    return inverse_cdf_acc(r, n, m, acc, dn, dm);
+    return inverse_cdf_acc(r, n, m, acc, dn, dm, cu);
 }
 
 // (x_j, shift_j) of member j of the group: shift = centred 9-sample mean of the climate-trend
@@ -275,13 +289,14 @@ qm_predict_kernel(const PredictParams p) {
     if (NT > 32) __syncthreads(); else __syncwarp();
 
     // ---- pass 2: rank → quantile → inverse CDF of the fitted group → output
-    const double dn = pp_denominator(n), dm = pp_denominator(m);
+    const Cunnane cu = cunnane_of(p);
+    const double dn = pp_denominator(n, cu), dm = pp_denominator(m, cu);
 #pragma unroll 4
     for (int e = 0; e < E; ++e) {
         const int j = tid * E + e;
         if (j >= n) break;
         const int rk = (int)rank_of[j];
-        const double val = inverse_cdf<T>(rk, n, m, S, dn, dm);
+        const double val = inverse_cdf<T>(rk, n, m, S, dn, dm, cu);
         double o;
         if constexpr (SHIFT) {
             double x, s;

@@ -305,9 +305,10 @@ __device__ __forceinline__ int cmp_members(const float* myX, int n, int a, int b
 
 // mapped value of 1-based rank rk: the fitted order statistic itself when the lengths agree,
 // else the Cunnane interpolation / OLS tails, read from the state record in global memory
-static __device__ __noinline__ float mapped_value_general(const float* __restrict__ S, int rk, int n, int m) {
+static __device__ __noinline__ float mapped_value_general(const PredictParams& p, const float* __restrict__ S, int rk, int n, int m) {
     auto Sat = [&](int i) -> double { return (double)__ldg(S + i); };
-    return (float)inverse_cdf_acc(rk, n, m, Sat, pp_denominator(n), pp_denominator(m));
+    const Cunnane cu = cunnane_of(p);
+    return (float)inverse_cdf_acc(rk, n, m, Sat, pp_denominator(n, cu), pp_denominator(m, cu), cu);
 }
 
 // ---------------------------------------------------------------- predict
@@ -515,7 +516,7 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
         for (int j = j0; j < j1; ++j) {
             const int rk = (int)Xu[skew(j)];
             if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
-            finish(j, same ? __ldg(S + rk - 1) : mapped_value_general(S, rk, n, m));
+            finish(j, same ? __ldg(S + rk - 1) : mapped_value_general(p, S, rk, n, m));
         }
     } else {
         // every other case (ties / swapped pairs / T_pred != T_fit / rank instrumentation): the exact
@@ -564,7 +565,7 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
                 const int pos = j0 + e0 + d;
                 if (pos < n) {
                     if (p.rank_out) p.rank_out[(int64_t)rg[member[d]] * p.ld_out + c] = rk[d];
-                    finish((int)member[d], same ? val[d] : mapped_value_general(S, rk[d], n, m));
+                    finish((int)member[d], same ? val[d] : mapped_value_general(p, S, rk[d], n, m));
                 }
             }
         }

@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -213,7 +215,7 @@ def qm_fit(y: torch.Tensor, sort_table: GroupTable, *, valid=None, X=None, mean_
 
 def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, return_anoms: bool = False,
                roll_nbr: np.ndarray | None = None, out_dtype=None, want_rank: bool = False, out=None,
-               climo_gid: np.ndarray | None = None):
+               climo_gid: np.ndarray | None = None, cunnane=None):
     """predict: quantile-map every (cell, group) of ``X`` through the fitted CDFs.
 
     ``table`` = mapping groups of the prediction index; group g uses the fitted group with
@@ -263,6 +265,7 @@ def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, r
                                   _ptr(st.sorted_state), st.state_ld,
                                   _ptr(x_climo), _ptr(y_climo), ld_climo,
                                   int(bool(return_anoms)), _ptr(nbr_dev),
+                                  ctypes.byref(cunnane) if cunnane is not None else None,
                                   _ptr(out), _TORCH_CODE[out.dtype], ld_out, _ptr(rank),
                                   _ptr(st.valid), _ptr(st.nonfinite), _stream()), 'sdb_qm_predict')
     return (out, rank) if want_rank else out
@@ -270,7 +273,7 @@ def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, r
 
 def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_query: torch.Tensor, k: int, *,
                    thresh=None, rand_idx=None, out_dtype=None, want_idx: bool = False, valid=None,
-                   nonfinite=None):
+                   nonfinite=None, logistic_C: float = 1.0):
     """PureAnalog / AnalogRegression fit+predict for all cells (gard.py:58-87, 152-224, 273-364).
 
     X_train [T, p, C], y_train [T, C], X_query [Tq, p, C] → out [Tq, 3, C]."""
@@ -295,7 +298,7 @@ def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_qu
         rand_idx = torch.as_tensor(np.ascontiguousarray(rand_idx, dtype=np.int32)).to(dev)
     _lib.check(lib.sdb_analog_predict(kind, _ptr(X_train), _ptr(y_train), _ptr(X_query), _code(X_train), C, C,
                                       T, Tq, p, k, int(thresh is not None),
-                                      float(thresh) if thresh is not None else 0.0, _ptr(rand_idx),
+                                      float(thresh) if thresh is not None else 0.0, float(logistic_C), _ptr(rand_idx),
                                       _ptr(out), _TORCH_CODE[od], C, _ptr(idx), _ptr(valid), _ptr(nonfinite),
                                       _stream()), 'sdb_analog_predict')
     return (out, idx) if want_idx else out

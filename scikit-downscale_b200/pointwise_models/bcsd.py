@@ -13,7 +13,7 @@ from .. import _lib, engine
 from .base import TimeSynchronousDownscaler, cuda_device, series_to_device
 from .groupers import (DAY_GROUPER, MONTH_GROUPER, PaddedDOYGrouper, grouper_keys, groups_from_keys,
                        padded_doy_groups, rolling_neighbours)
-from .quantile import check_qt_kwargs
+from .quantile import check_qt_kwargs, cunnane_opts
 from .utils import default_none_kwargs
 
 
@@ -55,6 +55,10 @@ class BcsdBase(TimeSynchronousDownscaler):
         if qm.get('detrend', False):
             raise NotImplementedError('qm_kwargs detrend=True is not on the B200 path yet')
         check_qt_kwargs(qm.get('qt_kwargs'))
+
+    def _cunnane(self):
+        """qm_kwargs['qt_kwargs'] → CunnaneTransformer settings of every group's mapper (bcsd.py:65-67)."""
+        return cunnane_opts(default_none_kwargs(self.qm_kwargs).get('qt_kwargs'))
 
     # ------------------------------------------------------------------ group tables (host, exact)
     def _fit_tables(self, index):
@@ -105,7 +109,8 @@ class BcsdBase(TimeSynchronousDownscaler):
             raise ValueError('shape of climo is not equal to input array')
         table, nbr = self._predict_tables(index)
         return engine.qm_predict(self._state, X, table, self._mode, return_anoms=self.return_anoms,
-                                 roll_nbr=nbr, out_dtype=out_dtype, want_rank=want_rank, out=out)
+                                 roll_nbr=nbr, out_dtype=out_dtype, want_rank=want_rank, out=out,
+                                 cunnane=self._cunnane())
 
     # ------------------------------------------------------------------ host arrays: chunked H2D → kernels → D2H
     @staticmethod
@@ -203,7 +208,8 @@ class BcsdBase(TimeSynchronousDownscaler):
                 if o_free[b] is not None:
                     comp.wait_event(o_free[b])
                 engine.qm_predict(st.cells(c0, c1), buf_x[b][:, :w], table, self._mode,
-                                  return_anoms=self.return_anoms, roll_nbr=nbr, out=buf_o[b][:, :w])
+                                  return_anoms=self.return_anoms, roll_nbr=nbr, out=buf_o[b][:, :w],
+                                  cunnane=self._cunnane())
                 done = torch.cuda.Event()
                 done.record(comp)
                 x_free[b] = done

@@ -64,11 +64,16 @@ class AnalogBase(RegressorMixin, BaseEstimator):
         pass
 
     def _check_finite(self):
-        if int(self._nonfinite.item()) != 0:
+        flags = int(self._nonfinite.item())
+        if flags != 0:
             self._nonfinite.zero_()
-            raise ValueError('Input contains NaN or infinity.')
+            if flags & 1:
+                raise ValueError('Input contains NaN or infinity.')
+            # gard.py:208-209: LogisticRegression.fit on a timestep whose analogs are all at or below thresh
+            raise ValueError('This solver needs samples of at least 2 classes in the data, but the data '
+                             'contains only one class: 0')
 
-    def _run(self, kind, k, X, out_dtype, thresh=None, rand_idx=None, want_idx=False):
+    def _run(self, kind, k, X, out_dtype, thresh=None, rand_idx=None, want_idx=False, logistic_C=1.0):
         if not hasattr(self, '_Xtr'):
             raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
                                  "appropriate arguments before using this estimator.")
@@ -79,7 +84,7 @@ class AnalogBase(RegressorMixin, BaseEstimator):
             X = X.to(self._Xtr.dtype)
         return engine.analog_predict(kind, self._Xtr, self._ytr, X, k, thresh=thresh, rand_idx=rand_idx,
                                      out_dtype=out_dtype, want_idx=want_idx, valid=self._valid,
-                                     nonfinite=self._nonfinite)
+                                     nonfinite=self._nonfinite, logistic_C=logistic_C)
 
     # ---- per-cell API
     def fit(self, X, y):
@@ -106,7 +111,9 @@ class AnalogBase(RegressorMixin, BaseEstimator):
 
 class AnalogRegression(AnalogBase):
     """AnalogRegression (gard.py:101-224): k analogs → OLS → prediction, exceedance
-    probability (1.0 without ``thresh``) and in-sample RMSE."""
+    probability and in-sample RMSE.  With ``thresh`` the exceedance probability is P(class 0) of
+    the per-timestep logistic regression (gard.py:205-212; the reference's lbfgs solution to its
+    tol = 1e-4, here the exact optimum) and the OLS uses the analogs above ``thresh`` only."""
 
     def __init__(self, n_analogs=200, thresh=None, kdtree_kwargs=None, query_kwargs=None,
                  logistic_kwargs=None, lr_kwargs=None):
@@ -118,13 +125,24 @@ class AnalogRegression(AnalogBase):
         self.lr_kwargs = lr_kwargs
 
     def predict_batched(self, X: torch.Tensor, out_dtype=None, want_idx=False, **_):
-        if self.thresh is not None:
-            raise NotImplementedError('AnalogRegression(thresh=...) needs the per-step logistic fit; '
-                                      'it is not on the B200 path yet (SURVEY.md §8(f) row 4)')
+        # logistic_kwargs (gard.py:171-172): the exceedance model is solved to its optimum on the device,
+        # so only what defines the objective matters — C; solver tolerances are accepted and ignored
+        C_reg = 1.0
+        for k, v in default_none_kwargs(self.logistic_kwargs).items():
+            if k == 'C':
+                C_reg = float(v)
+            elif k in ('tol', 'max_iter', 'n_jobs', 'verbose', 'random_state', 'warm_start'):
+                pass
+            elif (k, v) in (('penalty', 'l2'), ('fit_intercept', True), ('solver', 'lbfgs'), ('dual', False),
+                            ('class_weight', None), ('intercept_scaling', 1), ('l1_ratio', None)):
+                pass
+            else:
+                raise NotImplementedError(f'logistic_kwargs {k}={v!r} is not supported on the B200 path')
         for k, v in default_none_kwargs(self.lr_kwargs).items():
             if not (k == 'fit_intercept' and v) and not (k in ('copy_X', 'n_jobs', 'tol')) and not (k == 'positive' and not v):
                 raise NotImplementedError(f'lr_kwargs {k}={v!r} is not supported on the B200 path')
-        return self._run(_lib.ANALOG_REGRESSION, self.k_, X, out_dtype, want_idx=want_idx)
+        return self._run(_lib.ANALOG_REGRESSION, self.k_, X, out_dtype, thresh=self.thresh, want_idx=want_idx,
+                         logistic_C=C_reg)
 
 
 class PureAnalog(AnalogBase):

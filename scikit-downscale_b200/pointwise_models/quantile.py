@@ -1,9 +1,8 @@
 """QuantileMapper — drop-in for skdownscale.pointwise_models.QuantileMapper
 (skdownscale/pointwise_models/quantile.py:46-157), executed on the GPU.
 
-Only the default configuration of the reference's CunnaneTransformer is on the hot path
-(alpha = beta = 0.4, extrapolate='both', n_endpoints=10; quantile.py:420-432); other
-settings and ``detrend=True`` raise NotImplementedError (SURVEY.md §8(f) "next").
+``qt_kwargs`` (alpha, beta, extrapolate, n_endpoints of the reference's CunnaneTransformer,
+quantile.py:420-432) travel to the kernels as ``sdb_cunnane_opts``.
 """
 
 from __future__ import annotations
@@ -20,13 +19,28 @@ from .utils import default_none_kwargs
 _QT_DEFAULTS = {'alpha': 0.4, 'beta': 0.4, 'extrapolate': 'both', 'n_endpoints': 10}
 
 
-def check_qt_kwargs(qt_kwargs):
+def cunnane_opts(qt_kwargs):
+    """CunnaneTransformer(**qt_kwargs) (quantile.py:420-432) as the C-ABI option block, or None for
+    the defaults.  Unknown keywords raise like the reference's constructor would."""
+    kw = dict(_QT_DEFAULTS)
     for k, v in default_none_kwargs(qt_kwargs).items():
         if k not in _QT_DEFAULTS:
             raise TypeError(f"CunnaneTransformer.__init__() got an unexpected keyword argument '{k}'")
-        if v != _QT_DEFAULTS[k]:
-            raise NotImplementedError(f'qt_kwargs {k}={v!r}: only the default Cunnane settings '
-                                      f'{_QT_DEFAULTS} run on the B200 path')
+        kw[k] = v
+    if kw == _QT_DEFAULTS:
+        return None
+    if kw['extrapolate'] not in _lib.EXTRAPOLATE:
+        raise ValueError(f"unknown value for extrapolate: {kw['extrapolate']}")
+    if int(kw['n_endpoints']) < 1:
+        raise ValueError('n_endpoints must be >= 1')
+    # quantile.py:462 builds the CDF with plotting_positions(len(X)) — the transformer's own alpha / beta
+    # never reach it, so the reference always maps with 0.4 / 0.4; accepted and (like there) without effect
+    float(kw['alpha']), float(kw['beta'])
+    return _lib.CunnaneOpts(0.4, 0.4, int(kw['n_endpoints']), _lib.EXTRAPOLATE[kw['extrapolate']])
+
+
+def check_qt_kwargs(qt_kwargs):
+    cunnane_opts(qt_kwargs)
 
 
 def whole_series_table(n_rows: int) -> engine.GroupTable:
@@ -55,7 +69,7 @@ class QuantileMapper(TransformerMixin, BaseEstimator):
         if not hasattr(self, '_state'):
             raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet.")
         return engine.qm_predict(self._state, X, whole_series_table(X.shape[0]), _lib.MODE_QM,
-                                 out_dtype=out_dtype, want_rank=want_rank)
+                                 out_dtype=out_dtype, want_rank=want_rank, cunnane=cunnane_opts(self.qt_kwargs))
 
     # ---- per-cell API of the reference (one series)
     def fit(self, X, y=None):

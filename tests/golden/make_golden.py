@@ -72,7 +72,12 @@ def _cell_loop(model, Xtr, ytr, Xp, index_fit=None, index_pred=None, n_outputs=1
     return out
 
 
+ONLY = [a for a in sys.argv[1:]]          # optional name prefixes: regenerate just those files
+
+
 def save(name, **arrays):
+    if ONLY and not any(name.startswith(o) for o in ONLY):
+        return
     np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
     print('wrote', name, {k: getattr(v, 'shape', None) for k, v in arrays.items()})
 
@@ -107,6 +112,26 @@ def main():
             out[:, c] = QuantileMapper().fit(ytr[:, c:c + 1]).transform(Xp[:, c:c + 1])[:, 0]
         save(name, ytr=ytr, Xp=Xp, out=out)
 
+    # non-default CunnaneTransformer settings through qt_kwargs (quantile.py:420-432)
+    QT_VARIANTS = {
+        'ab': dict(alpha=0.3, beta=0.5, n_endpoints=5),
+        'none': dict(extrapolate=None),
+        'min': dict(extrapolate='min', n_endpoints=4),
+        'max': dict(extrapolate='max', alpha=0.0, beta=1.0),
+        '1to1': dict(extrapolate='1to1'),
+    }
+
+    def qm_qt_case(tag, qt, Tf, Tp, C, seed):
+        _, ytr, _ = synth.temperature(Tf, C, seed)
+        _, _, Xp = synth.temperature(Tp, C, seed + 100)
+        out = np.empty((Tp, C), dtype=np.float64)
+        for c in range(C):
+            out[:, c] = QuantileMapper(qt_kwargs=qt).fit(ytr[:, c:c + 1]).transform(Xp[:, c:c + 1])[:, 0]
+        save(f'qm_qt_{tag}', ytr=ytr, Xp=Xp, out=out)
+
+    for tag, qt in QT_VARIANTS.items():
+        qm_qt_case(tag, qt, 365, 1000, 2, 16)           # T_pred > T_fit: both tails are reached
+
     qm_case('qm_equal_len', 730, 730, 3, 10)
     qm_case('qm_pred_longer', 365, 1000, 3, 11)      # exercises both OLS tails
     qm_case('qm_pred_shorter', 1000, 300, 3, 12)
@@ -138,6 +163,8 @@ def main():
     bcsd_t_case('bcsd_t_month_anoms', 1461, 1461, 4, 20, nan_cells=(2,))
     bcsd_t_case('bcsd_t_month_abs', 1461, 1461, 3, 21, return_anoms=False)
     bcsd_t_case('bcsd_t_month_future', 1461, 2192, 3, 22, start_pred='1985-01-01')   # T_pred > T_fit → tails
+    bcsd_t_case('bcsd_t_month_future_qt', 1096, 1826, 2, 25, start_pred='1984-01-01',
+                qm_kwargs={'qt_kwargs': dict(alpha=0.3, beta=0.5, n_endpoints=5, extrapolate='max')})
     bcsd_t_case('bcsd_t_month_f64', 1096, 1096, 2, 23, dtype=np.float64)
     bcsd_t_case('bcsd_t_month_30yr', 10950, 10950, 1, 0)                              # BASELINE config[0]
     bcsd_t_case('bcsd_t_nasanex', 1096, 1096, 2, 24, start_fit='1980-01-01',
@@ -203,6 +230,30 @@ def main():
 
     ar_case('analogreg_k10', 300, 120, 2, 50, 10)
     ar_case('analogreg_k200', 400, 40, 1, 51, 200)
+
+    # AnalogRegression(thresh=...) (gard.py:201-215).  Query steps whose analogs are ALL at or below the
+    # threshold make the reference raise, so they are dropped from the query set (the error path has
+    # its own test).  `out64` = the reference with its default lbfgs tolerance (1e-4), `out64_tight` =
+    # the same call with logistic_kwargs tol=1e-12 (the optimum the default run approximates).
+    def ar_thresh_case(name, T, Tq, seed, n_analogs, thresh, C_reg=1.0):
+        Xtr, ytr, Xq = synth.analog(T, Tq, 1, 3, seed)
+        A, Q = Xtr[..., 0].astype(np.float64), Xq[..., 0].astype(np.float64)
+        k = min(n_analogs, T)
+        d2 = ((Q[:, None, :] - A[None, :, :]) ** 2).sum(-1)
+        inds = np.argsort(d2, axis=1, kind='stable')[:, :k]
+        keep = (ytr[:, 0][inds] > thresh).sum(axis=1) >= 1
+        Xq = Xq[keep]
+        kws = {} if C_reg == 1.0 else {'C': C_reg}
+        m = AnalogRegression(n_analogs=n_analogs, thresh=thresh, logistic_kwargs=kws or None)
+        out64 = np.asarray(m.fit(_df(Xtr[..., 0]), _df(ytr[:, 0])).predict(_df(Xq[..., 0])))
+        m = AnalogRegression(n_analogs=n_analogs, thresh=thresh, logistic_kwargs=dict(kws, tol=1e-12, max_iter=10000))
+        tight = np.asarray(m.fit(_df(Xtr[..., 0]), _df(ytr[:, 0])).predict(_df(Xq[..., 0])))
+        save(name, Xtr=Xtr, ytr=ytr, Xq=Xq, out64=out64[:, :, None], out64_tight=tight[:, :, None],
+             thresh=np.float64(thresh), C_reg=np.float64(C_reg))
+
+    ar_thresh_case('analogreg_thresh_k20', 300, 200, 52, 20, -0.5)
+    ar_thresh_case('analogreg_thresh_k10_C', 300, 160, 54, 10, -0.8, C_reg=0.3)
+    ar_thresh_case('analogreg_thresh_k200', 400, 60, 53, 200, 0.0)
 
     import sklearn
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:

@@ -94,6 +94,37 @@ def test_qm_golden(dev, golden, name):
         np.testing.assert_allclose(o, g['out'][:, c], rtol=1e-11, atol=1e-11)
 
 
+QT_VARIANTS = {          # the settings tests/golden/make_golden.py used for the qm_qt_* files
+    'ab': dict(alpha=0.3, beta=0.5, n_endpoints=5),
+    'none': dict(extrapolate=None),
+    'min': dict(extrapolate='min', n_endpoints=4),
+    'max': dict(extrapolate='max', alpha=0.0, beta=1.0),
+    '1to1': dict(extrapolate='1to1'),
+}
+
+
+@pytest.mark.parametrize('tag', sorted(QT_VARIANTS))
+def test_qm_cunnane_settings_golden(dev, golden, tag):
+    """QuantileMapper(qt_kwargs=...): plotting-position parameters, tail selection and end-point count
+    of the reference's CunnaneTransformer (quantile.py:420-432) against the live-reference vectors."""
+    g = golden(f'qm_qt_{tag}')
+    qt = QT_VARIANTS[tag]
+    pw = pm().PointWiseDownscaler(pm().QuantileMapper(qt_kwargs=qt))
+    pw.fit(g['ytr'])
+    got = pw.transform(g['Xp'])                                   # float32 tile kernels
+    assert_close(got, g['out'].astype(g['Xp'].dtype), scale=np.std(g['ytr']))
+    for c in range(g['Xp'].shape[1]):                             # per-cell API, float64 out
+        o = pm().QuantileMapper(qt_kwargs=qt).fit(g['ytr'][:, c:c + 1]).transform(g['Xp'][:, c:c + 1])[:, 0]
+        np.testing.assert_allclose(o, g['out'][:, c], rtol=1e-11, atol=1e-11)
+
+
+def test_qm_cunnane_bad_settings(dev):
+    with pytest.raises(TypeError, match='unexpected keyword'):
+        pm().QuantileMapper(qt_kwargs={'gamma': 1}).fit(np.arange(10.0).reshape(-1, 1))
+    with pytest.raises(ValueError, match='extrapolate'):
+        pm().QuantileMapper(qt_kwargs={'extrapolate': 'sideways'}).fit(np.arange(10.0).reshape(-1, 1))
+
+
 @pytest.mark.parametrize('n_fit,n_pred', [(1, 1), (2, 5), (255, 256), (256, 256), (257, 257), (1024, 1024),
                                           (1025, 1000), (4096, 4096), (4097, 5000), (10950, 10950), (16384, 16384)])
 def test_qm_sizes_vs_oracle(dev, n_fit, n_pred):
@@ -146,6 +177,7 @@ def _expected_rank_map(x, y):
     ('bcsd_t_month_anoms', {}),
     ('bcsd_t_month_abs', {'return_anoms': False}),
     ('bcsd_t_month_future', {}),
+    ('bcsd_t_month_future_qt', {'qm_kwargs': {'qt_kwargs': dict(alpha=0.3, beta=0.5, n_endpoints=5, extrapolate='max')}}),
     ('bcsd_t_month_f64', {}),
     ('bcsd_t_month_30yr', {}),
     ('bcsd_t_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
@@ -401,6 +433,39 @@ def test_analog_regression_golden(dev, golden, name, k):
     o = m.predict(pd.DataFrame(g['Xq'][..., 0]))
     assert list(o.columns) == ['pred', 'exceedance_prob', 'prediction_error']
     np.testing.assert_allclose(o.values, g['out64'][:, :, 0], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize('name,k', [('analogreg_thresh_k20', 20), ('analogreg_thresh_k10_C', 10),
+                                    ('analogreg_thresh_k200', 200)])
+def test_analog_regression_thresh_golden(dev, golden, name, k):
+    """AnalogRegression(thresh=...): prediction / RMSE to 1e-7 relative; exceedance probability to 1e-6
+    against the tightly converged reference and to 2e-3 against the reference's default lbfgs run
+    (stopped at tol = 1e-4 by scikit-learn, so only defined to that level)."""
+    g = golden(name)
+    th, C_reg = float(g['thresh']), float(g['C_reg'])
+    kw = {} if C_reg == 1.0 else {'logistic_kwargs': {'C': C_reg}}
+    m = pm().AnalogRegression(n_analogs=k, thresh=th, **kw)
+    m.fit(pd.DataFrame(g['Xtr'][..., 0]), pd.DataFrame(g['ytr'][:, 0]))
+    o = m.predict(pd.DataFrame(g['Xq'][..., 0])).values
+    ref, tight = g['out64'][:, :, 0], g['out64_tight'][:, :, 0]
+    np.testing.assert_allclose(o[:, [0, 2]], ref[:, [0, 2]], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(o[:, 1], tight[:, 1], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(o[:, 1], ref[:, 1], rtol=0, atol=2e-3)
+    # batched wrapper path (float32 in / out) against the oracle
+    pw = pm().PointWiseDownscaler(pm().AnalogRegression(n_analogs=k, thresh=th, **kw))
+    pw.fit(g['Xtr'], g['ytr'])
+    got = pw.predict(g['Xq'])
+    want = oracle.analog_regression_predict(g['Xtr'][..., 0], g['ytr'][:, 0], g['Xq'][..., 0], k, thresh=th,
+                                            logistic_C=C_reg)
+    np.testing.assert_allclose(got[:, :, 0], want.astype(np.float32), rtol=2e-5, atol=2e-6)
+
+
+def test_analog_regression_thresh_one_class_raises(dev):
+    """All analogs of a query at or below thresh: the reference's LogisticRegression raises (gard.py:208-209)."""
+    Xtr, ytr, Xq = synth.analog(200, 20, 1, 3, seed=3)
+    m = pm().AnalogRegression(n_analogs=5, thresh=1e6).fit(pd.DataFrame(Xtr[..., 0]), pd.DataFrame(ytr[:, 0]))
+    with pytest.raises(ValueError, match='at least 2 classes'):
+        m.predict(pd.DataFrame(Xq[..., 0]))
 
 
 @pytest.mark.parametrize('p,k,T,Tq', [(1, 5, 700, 300), (3, 10, 2500, 600), (3, 16, 1100, 257), (3, 17, 900, 100),

@@ -22,6 +22,25 @@ def test_qm_known_answer(golden):
     _close(out, g['out'][:, 0])
 
 
+QT_VARIANTS = {          # the settings tests/golden/make_golden.py used for the qm_qt_* files
+    'ab': dict(alpha=0.3, beta=0.5, n_endpoints=5),
+    'none': dict(extrapolate=None),
+    'min': dict(extrapolate='min', n_endpoints=4),
+    'max': dict(extrapolate='max', alpha=0.0, beta=1.0),
+    '1to1': dict(extrapolate='1to1'),
+}
+
+
+@pytest.mark.parametrize('tag', sorted(QT_VARIANTS))
+def test_qm_cunnane_settings(golden, tag):
+    """QuantileMapper(qt_kwargs=...) — non-default CunnaneTransformer settings (quantile.py:420-432)."""
+    g = golden(f'qm_qt_{tag}')
+    for c in range(g['Xp'].shape[1]):
+        st = oracle.quantile_mapper_fit(g['ytr'][:, c])
+        _close(oracle.quantile_mapper_transform(g['Xp'][:, c], st, **QT_VARIANTS[tag]), g['out'][:, c],
+               rtol=1e-13, atol=1e-13)
+
+
 @pytest.mark.parametrize('name', ['qm_equal_len', 'qm_pred_longer', 'qm_pred_shorter', 'qm_ties',
                                   'qm_f64', 'qm_tiny'])
 def test_qm_cases(golden, name):
@@ -60,6 +79,7 @@ def test_padded_doy_grouper(golden):
     ('bcsd_t_month_anoms', {}),
     ('bcsd_t_month_abs', {'return_anoms': False}),
     ('bcsd_t_month_future', {}),
+    ('bcsd_t_month_future_qt', {'qt_kwargs': dict(alpha=0.3, beta=0.5, n_endpoints=5, extrapolate='max')}),
     ('bcsd_t_month_f64', {}),
     ('bcsd_t_month_30yr', {}),
     ('bcsd_t_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
@@ -83,7 +103,7 @@ def test_bcsd_temperature(golden, name, kw):
         how = 'frame' if spec['time_grouper'] == 'daily_nasa-nex' else 'groupby'
         st = oracle.bcsd_temperature_fit(g['Xtr'][:, c], g['ytr'][:, c], fit_groups, how)
         o = oracle.bcsd_temperature_predict(st, g['Xp'][:, c], roll_groups, qm_groups,
-                                            kw.get('return_anoms', True))
+                                            kw.get('return_anoms', True), qt=kw.get('qt_kwargs'))
         _close(o, ref[:, c], rtol=0, atol=2e-12 * max(1.0, scale))
 
 
@@ -144,3 +164,28 @@ def test_analog_regression(golden, name, k):
         _close(o, g['out64'][:, :, c], rtol=1e-9, atol=1e-10)
     out = oracle.pointwise_fit_predict({'name': 'AnalogRegression', 'n_analogs': k}, g['Xtr'], g['ytr'], g['Xq'])
     _close(out, g['out'], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('name,k', [('analogreg_thresh_k20', 20), ('analogreg_thresh_k10_C', 10),
+                                    ('analogreg_thresh_k200', 200)])
+def test_analog_regression_thresh(golden, name, k):
+    """AnalogRegression(thresh=...) (gard.py:201-215): prediction and RMSE (least squares on the analogs
+    above the threshold, minimum norm when only a few exceed) to 1e-9; the exceedance probability to
+    1e-7 against the reference run with a tight lbfgs tolerance, and to 2e-3 against the reference's
+    DEFAULT run — whose own solver stops at a gradient of 1e-4, i.e. is only defined to that level."""
+    g = golden(name)
+    o = oracle.analog_regression_predict(g['Xtr'][..., 0], g['ytr'][:, 0], g['Xq'][..., 0], k,
+                                         thresh=float(g['thresh']), logistic_C=float(g['C_reg']))
+    ref, tight = g['out64'][:, :, 0], g['out64_tight'][:, :, 0]
+    _close(o[:, [0, 2]], ref[:, [0, 2]], rtol=1e-9, atol=1e-10)
+    _close(o[:, 1], tight[:, 1], rtol=0, atol=1e-7)
+    _close(o[:, 1], ref[:, 1], rtol=0, atol=2e-3)
+    assert ((ref[:, 1] > 0) & (ref[:, 1] < 1)).sum() > 20        # the logistic branch is exercised
+    if k < 200:
+        assert (ref[:, 1] == 1.0).sum() > 0                      # ... and the all-exceed shortcut
+
+
+def test_analog_regression_thresh_one_class():
+    Xtr, ytr, Xq = synth.analog(200, 20, 1, 3, seed=3)
+    with pytest.raises(ValueError, match='at least 2 classes'):
+        oracle.analog_regression_predict(Xtr[..., 0], ytr[:, 0], Xq[..., 0], 5, thresh=1e6)
