@@ -187,6 +187,51 @@ int sdb_analog_predict(int kind, const void* X_train, const void* y_train, const
                        void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
                        const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
 
+/*
+ * 1-based rank of every value among its (cell, group) series: the tie-max rank of the quantile map
+ * (ordinal = 0; ties share the highest rank, quantile.py:138,488) or the position in (value, time
+ * index) order (ordinal = 1; what `np.argsort` yields on tie-free data, quantile.py:239,607).
+ *   rank_out[t * ld_rank + c], int32; cells masked by cell_valid get 0.
+ */
+int sdb_series_rank(const void* X, int dtype, int64_t ld, int64_t n_cells,
+                    const int32_t* rows, const int32_t* len, int n_groups, int max_len,
+                    int ordinal, int32_t* rank_out, int64_t ld_rank,
+                    const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+/* CDF-to-CDF regressors */
+#define SDB_QMR_REGRESSOR         0   /* QuantileMappingReressor.predict   quantile.py:224-266 */
+#define SDB_QMR_EDCDF_DIFFERENCE  1   /* EquidistantCdfMatcher.predict, kind='difference'   quantile.py:594-636 */
+#define SDB_QMR_EDCDF_RATIO       2   /* ... kind='ratio' (max_ratio=None) */
+
+/*
+ * Synthetic frame points of the two fitted CDFs of every cell (`_calc_extrapolated_cdf`,
+ * quantile.py:311-388): frame[c * 4 + {0, 1, 2, 3}] = lower / upper frame value of sorted X, then of
+ * sorted y — the OLS line through the n_endpoints end points evaluated at pp = -1e20 / +1e20 on the
+ * tails `extrapolate` names, the repeated end value otherwise.  sorted_x / sorted_y: the fitted
+ * states of sdb_qm_fit on ONE whole-series group (cell record = the n_fit sorted values).
+ */
+int sdb_qmr_frame(const void* sorted_x, const void* sorted_y, int dtype, int64_t state_ld,
+                  int64_t n_cells, int n_fit, int extrapolate, int n_endpoints,
+                  double* frame, const uint8_t* cell_valid, void* stream);
+
+/*
+ * QuantileMappingReressor / EquidistantCdfMatcher predict for every cell and time step:
+ *   REGRESSOR         out = interp(interp(x, X_cdf.vals, X_cdf.pp), y_cdf.pp, y_cdf.vals)
+ *   EDCDF_DIFFERENCE  q = Cunnane position of x among the T_pred values of its cell (rank, ordinal);
+ *                     out = y_cdf(q) + (x - X_cdf(q));     EDCDF_RATIO  out = y_cdf(q) * (x / X_cdf(q))
+ * one_to_one: extrapolate='1to1' — values outside the fitted X range keep their distance to the
+ * range end (quantile.py:268-309).  The result has the dtype of X (out_dtype == dtype).
+ * Under 'min' / 'max' / 'both' the reference's own results OUTSIDE the fitted range are ill-conditioned
+ * (a difference of two ~1e21 numbers, quantile.py:17-18,375-386): they are computed the same way but
+ * are not comparable bit for bit.  Replaces quantile.py:224-266, 594-636.
+ */
+int sdb_qmr_predict(int kind, const void* X, int dtype, int64_t ld, int64_t n_cells, int t_pred,
+                    const void* sorted_x, const void* sorted_y, int64_t state_ld, int n_fit,
+                    const double* frame, int extrapolate, int one_to_one,
+                    const int32_t* rank, int64_t ld_rank,
+                    void* out, int out_dtype, int64_t ld_out,
+                    const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

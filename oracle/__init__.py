@@ -16,7 +16,8 @@ Parity pin: the oracle is asserted against the LIVE reference estimators
 vectors committed under ``tests/golden/`` (generator:
 ``tests/golden/make_golden.py``) and against the reference's own known-answer
 tests (``skdownscale/test/test_pointwise_models.py:81-90`` quantile mapper,
-``:302-312`` padded DOY grouper) — see ``tests/test_oracle_golden.py``.
+``:302-312`` padded DOY grouper, ``:323-344`` EquidistantCdfMatcher) — see
+``tests/test_oracle_golden.py``.
 """
 
 from .groupers import (  # noqa: F401
@@ -27,7 +28,12 @@ from .groupers import (  # noqa: F401
 )
 from .quantile import (  # noqa: F401
     cunnane_inverse,
+    edcdf_predict,
+    extended_cdf,
     plotting_positions,
+    qm_regressor_fit,
+    qm_regressor_predict,
+    qmr_well_conditioned,
     quantile_mapper_fit,
     quantile_mapper_transform,
     rank_max_ties,

@@ -24,6 +24,7 @@ class CunnaneOpts(ctypes.Structure):
     _fields_ = [('alpha', c_double), ('beta', c_double), ('n_endpoints', ctypes.c_int32), ('extrapolate', ctypes.c_int32)]
 
 
+QMR_REGRESSOR, QMR_EDCDF_DIFFERENCE, QMR_EDCDF_RATIO = 0, 1, 2
 ANALOG_BEST, ANALOG_SAMPLE, ANALOG_WEIGHT, ANALOG_MEAN, ANALOG_REGRESSION = 0, 1, 2, 3, 4
 
 # every symbol include/sdb.h declares: (restype, argtypes)
@@ -51,6 +52,16 @@ SIGNATURES = {
                                    c_int, c_double, c_double, c_void_p,
                                    c_void_p, c_int, c_int64, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
+    'sdb_series_rank': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
+                                c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'sdb_qmr_frame': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_void_p]),
+    'sdb_qmr_predict': (c_int, [c_int, c_void_p, c_int, c_int64, c_int64, c_int,
+                                c_void_p, c_void_p, c_int64, c_int,
+                                c_void_p, c_int, c_int,
+                                c_void_p, c_int64,
+                                c_void_p, c_int, c_int64,
+                                c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -137,6 +137,7 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
     p.roll_nbr = roll_nbr; p.out = out; p.ld_out = ld_out; p.rank_out = rank_out; p.valid = cell_valid; p.nonfinite = nonfinite;
     p.mode = mode; p.out_f64 = (out_dtype == SDB_F64); p.n_groups = n_groups;
     p.no_vec = (g_debug_flags & 2) != 0;
+    p.rank_only = 0; p.rank_ordinal = 0;
     p.alpha = 0.4; p.beta = 0.4; p.n_endpoints = 10; p.extrap_lo = 1; p.extrap_hi = 1;   // quantile.py:420-432 defaults
     if (cunnane) {
         if (cunnane->n_endpoints < 1) return sdb_fail(SDB_E_INVALID, "sdb_qm_predict: n_endpoints must be >= 1");
@@ -160,4 +161,29 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
         case 16384: return qm_predict_np16384(dtype, kind, p, st);
     }
     return sdb_fail(SDB_E_UNSUPPORTED, "sdb_qm_predict: group length %d > %d", max_len, SDB_MAX_GROUP_LEN);
+}
+
+extern "C" int sdb_series_rank(const void* X, int dtype, int64_t ld, int64_t n_cells,
+                               const int32_t* rows, const int32_t* len, int n_groups, int max_len,
+                               int ordinal, int32_t* rank_out, int64_t ld_rank,
+                               const uint8_t* cell_valid, int32_t* nonfinite, void* stream) {
+    if (!X || !rows || !len || !rank_out) return sdb_fail(SDB_E_INVALID, "sdb_series_rank: NULL pointer");
+    if (n_cells <= 0 || n_groups <= 0 || max_len <= 0 || ld < n_cells || ld_rank < n_cells)
+        return sdb_fail(SDB_E_INVALID, "sdb_series_rank: bad shape");
+    if (ld >= (1LL << 32) || ld_rank >= (1LL << 32)) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_series_rank: row stride must be below 2^32 elements");
+    if (dtype != SDB_F32 && dtype != SDB_F64) return sdb_fail(SDB_E_INVALID, "sdb_series_rank: bad dtype %d", dtype);
+    PredictParams p;
+    memset(&p, 0, sizeof(p));
+    p.X = X; p.ld = ld; p.C = n_cells; p.rows = rows; p.len = len; p.max_len = max_len;
+    p.rank_out = rank_out; p.ld_out = ld_rank; p.valid = cell_valid; p.nonfinite = nonfinite;
+    p.mode = SDB_MODE_QM; p.n_groups = n_groups; p.rank_only = 1; p.rank_ordinal = ordinal != 0;
+    p.alpha = 0.4; p.beta = 0.4; p.n_endpoints = 10; p.extrap_lo = 1; p.extrap_hi = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (pick_np(max_len)) {
+        case 256:   return qm_predict_np256(dtype, KIND_RAW, p, st);
+        case 1024:  return qm_predict_np1024(dtype, KIND_RAW, p, st);
+        case 4096:  return qm_predict_np4096(dtype, KIND_RAW, p, st);
+        case 16384: return qm_predict_np16384(dtype, KIND_RAW, p, st);
+    }
+    return sdb_fail(SDB_E_UNSUPPORTED, "sdb_series_rank: group length %d > %d", max_len, SDB_MAX_GROUP_LEN);
 }

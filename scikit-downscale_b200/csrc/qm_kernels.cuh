@@ -122,6 +122,9 @@ struct PredictParams {
     // points of the OLS extrapolation, and which tails extrapolate (otherwise np.interp clamps)
     double alpha, beta;
     int n_endpoints, extrap_lo, extrap_hi;
+    // sdb_series_rank: stop after the ranking pass and write rank_out only; rank_ordinal = 1-based
+    // position in the (value, time index) order instead of the tie-max rank
+    int rank_only, rank_ordinal;
 };
 
 // kernel flavours (compile-time): what the rank keys are
@@ -244,15 +247,15 @@ qm_predict_kernel(const PredictParams p) {
     const int32_t* rg = p.rows + (int64_t)g * p.max_len;
     if (p.valid && !p.valid[c]) {
         for (int j = tid; j < n; j += NT) {
-            store_out(p.out, p.out_f64, (int64_t)rg[j] * p.ld_out + c, (double)NAN);
+            if (p.out) store_out(p.out, p.out_f64, (int64_t)rg[j] * p.ld_out + c, (double)NAN);
             if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = 0;
         }
         return;
     }
     const T* X = (const T*)p.X;
-    const int sg = p.state_gid[g];
-    const int m = p.fit_len[sg];
-    const T* S = (const T*)p.state + c * p.state_ld + p.state_off[sg];
+    const int sg = p.rank_only ? 0 : p.state_gid[g];
+    const int m = p.rank_only ? n : p.fit_len[sg];
+    const T* S = p.rank_only ? nullptr : (const T*)p.state + c * p.state_ld + p.state_off[sg];
     double xc = 0.0, yc = 0.0;
     if (SHIFT) xc = (double)((const T*)p.x_climo)[(int64_t)sg * p.ld_climo + c];
     if (p.mode != SDB_MODE_QM && p.return_anoms) yc = (double)((const T*)p.y_climo)[(int64_t)sg * p.ld_climo + c];
@@ -280,7 +283,12 @@ qm_predict_kernel(const PredictParams p) {
     }
     sort_blocked<Item, E, NT>(v, tid, smem);
     int r[E];
-    tie_max_ranks<Item, E, NT>(v, tid, r, smem);
+    if (p.rank_ordinal) {
+#pragma unroll
+        for (int e = 0; e < E; ++e) r[e] = tid * E + e + 1;
+    } else {
+        tie_max_ranks<Item, E, NT>(v, tid, r, smem);
+    }
     if (NT > 32) __syncthreads();                       // scratch is about to be reused as rank_of
     uint16_t* rank_of = reinterpret_cast<uint16_t*>(smem) + (size_t)sub * NP;
 #pragma unroll
@@ -288,6 +296,10 @@ qm_predict_kernel(const PredictParams p) {
         if (v[e].i < (uint32_t)n) rank_of[v[e].i] = (uint16_t)r[e];
     if (NT > 32) __syncthreads(); else __syncwarp();
 
+    if (p.rank_only) {
+        for (int j = tid; j < n; j += NT) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = (int)rank_of[j];
+        return;
+    }
     // ---- pass 2: rank → quantile → inverse CDF of the fitted group → output
     const Cunnane cu = cunnane_of(p);
     const double dn = pp_denominator(n, cu), dm = pp_denominator(m, cu);

@@ -681,7 +681,10 @@ static int launch_fit_tile(const FitParams& f, cudaStream_t st) {
 template <int E, bool SHIFT>
 static int launch_predict_tile(const PredictParams& p, cudaStream_t st) {
     auto kern = qm_predict_tile_kernel<E, SHIFT>;
-    const size_t smem = predict_tile_smem<E>();
+#ifndef SDB_PRED_EXTRA_SMEM
+#define SDB_PRED_EXTRA_SMEM 0            // experiment builds: inflate the footprint to probe occupancy sensitivity
+#endif
+    const size_t smem = predict_tile_smem<E>() + SDB_PRED_EXTRA_SMEM;
     if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT), (unsigned)p.n_groups);
     kern<<<grid, TILE_THREADS, smem, st>>>(p);

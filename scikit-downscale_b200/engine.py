@@ -302,3 +302,49 @@ def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_qu
                                       _ptr(out), _TORCH_CODE[od], C, _ptr(idx), _ptr(valid), _ptr(nonfinite),
                                       _stream()), 'sdb_analog_predict')
     return (out, idx) if want_idx else out
+
+
+# ---------------------------------------------------------------------------------------------
+# CDF-to-CDF regressors (QuantileMappingReressor / EquidistantCdfMatcher, quantile.py:160-395, 556-636)
+# ---------------------------------------------------------------------------------------------
+def series_rank(X: torch.Tensor, table: GroupTable, *, ordinal: bool, valid=None, nonfinite=None) -> torch.Tensor:
+    """1-based rank of every value inside its (cell, group) series → int32 ``[T, C]``."""
+    lib = _lib.load()
+    ld = _check_2d(X, 'X')
+    T, C = X.shape
+    if table.max_len > lib.sdb_max_group_len():
+        raise NotImplementedError(f'series longer than {lib.sdb_max_group_len()} steps are not supported yet')
+    rows, length = table.device(X.device)
+    rank = torch.zeros((T, C), dtype=torch.int32, device=X.device)
+    _lib.check(lib.sdb_series_rank(_ptr(X), _code(X), ld, C, _ptr(rows), _ptr(length), table.n_groups,
+                                   table.rows.shape[1], int(ordinal), _ptr(rank), C, _ptr(valid), _ptr(nonfinite),
+                                   _stream()), 'sdb_series_rank')
+    return rank
+
+
+def qmr_frame(sx: QMFitted, sy: QMFitted, extrapolate: int, n_endpoints: int) -> torch.Tensor:
+    """Synthetic frame points of the fitted X / y CDFs of every cell → float64 ``[C, 4]``."""
+    lib = _lib.load()
+    n_fit = int(sx.sort_table.max_len)
+    frame = torch.empty((sx.n_cells, 4), dtype=torch.float64, device=sx.sorted_state.device)
+    _lib.check(lib.sdb_qmr_frame(_ptr(sx.sorted_state), _ptr(sy.sorted_state), _code(sx.sorted_state), sx.state_ld,
+                                 sx.n_cells, n_fit, extrapolate, n_endpoints, _ptr(frame), _ptr(sx.valid), _stream()),
+               'sdb_qmr_frame')
+    return frame
+
+
+def qmr_predict(kind: int, X: torch.Tensor, sx: QMFitted, sy: QMFitted, frame: torch.Tensor, extrapolate: int,
+                one_to_one: bool, rank: torch.Tensor | None = None) -> torch.Tensor:
+    lib = _lib.load()
+    ld = _check_2d(X, 'X')
+    T, C = X.shape
+    if C != sx.n_cells:
+        raise ValueError(f'X has {C} cells, the model was fitted on {sx.n_cells}')
+    if X.dtype != sx.dtype:
+        raise TypeError(f'X is {X.dtype}, the model was fitted on {sx.dtype}')
+    out = torch.empty((T, C), dtype=X.dtype, device=X.device)
+    _lib.check(lib.sdb_qmr_predict(kind, _ptr(X), _code(X), ld, C, T, _ptr(sx.sorted_state), _ptr(sy.sorted_state),
+                                   sx.state_ld, int(sx.sort_table.max_len), _ptr(frame), extrapolate, int(one_to_one),
+                                   _ptr(rank), C, _ptr(out), _code(X), C, _ptr(sx.valid), _ptr(sx.nonfinite), _stream()),
+               'sdb_qmr_predict')
+    return out

@@ -1,13 +1,14 @@
 """Drop-in surface of ``skdownscale.pointwise_models`` for the B200 hot path
 (skdownscale/pointwise_models/__init__.py:1-36).  Estimators outside the hot path
-(PureRegression, ZScoreRegressor, EquidistantCdfMatcher, ...) are not provided.
+(PureRegression, ZScoreRegressor, ...) are not provided; QuantileMappingReressor and
+EquidistantCdfMatcher are the first "next" row of SURVEY.md §8(f).
 """
 
 from .bcsd import BcsdPrecipitation, BcsdTemperature
 from .core import PointWiseDownscaler
 from .gard import AnalogRegression, PureAnalog
 from .groupers import DAY_GROUPER, MONTH_GROUPER, PaddedDOYGrouper
-from .quantile import QuantileMapper
+from .quantile import EquidistantCdfMatcher, QuantileMapper, QuantileMappingReressor
 
 __all__ = [
     'BcsdPrecipitation',
@@ -19,4 +20,6 @@ __all__ = [
     'MONTH_GROUPER',
     'PaddedDOYGrouper',
     'QuantileMapper',
+    'QuantileMappingReressor',
+    'EquidistantCdfMatcher',
 ]

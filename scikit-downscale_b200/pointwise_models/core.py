@@ -24,7 +24,7 @@ from .. import engine
 from .base import cuda_device
 from .bcsd import BcsdBase
 from .gard import AnalogBase
-from .quantile import QuantileMapper
+from .quantile import QuantileMapper, QuantileMappingReressor
 
 try:  # xarray is optional (absent in the build container)
     import xarray as xr
@@ -175,6 +175,10 @@ class PointWiseDownscaler:
                 model.fit_batched(x[:, 0], y[:, 0], bx.index, valid=valid)
             elif isinstance(model, AnalogBase):
                 model.fit_batched(x, y[:, 0], valid=valid)
+            elif isinstance(model, QuantileMappingReressor):
+                if x.shape[1] != 1:
+                    raise ValueError(f'X should have up to 1 features, found {x.shape[1]}')
+                model.fit_batched(x[:, 0], y[:, 0], valid=valid)
             else:
                 raise TypeError(f'{type(model).__name__} is not a B200-native estimator; PointWiseDownscaler '
                                 'has no per-cell Python fallback')
@@ -247,6 +251,10 @@ class PointWiseDownscaler:
                 raise ValueError('BCSD models need the time axis labels: pass time=<DatetimeIndex>')
             out = model.predict_batched(x[:, 0], bx.index)
             model._state.check_finite()
+            return self._wrap(out, bx)
+        if isinstance(model, QuantileMappingReressor):
+            out = model.predict_batched(x[:, 0])
+            model.check_fit()
             return self._wrap(out, bx)
         out = model.predict_batched(x)
         model._check_finite()

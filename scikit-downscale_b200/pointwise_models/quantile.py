@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 import torch
-from sklearn.base import BaseEstimator, TransformerMixin
+from sklearn.base import BaseEstimator, RegressorMixin, TransformerMixin
 from sklearn.exceptions import NotFittedError
 
 from .. import _lib, engine
@@ -93,3 +93,108 @@ class QuantileMapper(TransformerMixin, BaseEstimator):
         out = self.transform_batched(x, out_dtype=torch.float64)
         self._state.check_finite()
         return out.cpu().numpy().reshape(-1, 1)
+
+
+class QuantileMappingReressor(RegressorMixin, BaseEstimator):
+    """Transform features using quantile mapping — CDF of X onto the CDF of y
+    (quantile.py:160-395; the class name keeps the reference's spelling).
+
+    ``extrapolate`` in {None, 'min', 'max', 'both', '1to1'}, ``n_endpoints >= 2``.  Note for
+    'min' / 'max' / 'both': outside the fitted X range the reference interpolates through a
+    synthetic CDF point at pp = -1e20 / +1e20 (quantile.py:17-18), a cancellation of ~1e21-sized
+    numbers — those outputs are computed the same way here but carry no significant digits in
+    either implementation."""
+
+    _fit_attributes = ['_X_cdf', '_y_cdf']
+    _kind = _lib.QMR_REGRESSOR
+
+    def __init__(self, extrapolate=None, n_endpoints=10):
+        self.extrapolate = extrapolate
+        self.n_endpoints = n_endpoints
+        if self.n_endpoints < 2:
+            raise ValueError('Invalid number of n_endpoints, must be >= 2')
+
+    # ---- batched (all cells) API used by PointWiseDownscaler
+    def fit_batched(self, X: torch.Tensor, y: torch.Tensor, valid=None):
+        if self.extrapolate not in _lib.EXTRAPOLATE:
+            raise ValueError(f'unknown value for extrapolate: {self.extrapolate}')
+        n = X.shape[0]
+        need = 2 * self.n_endpoints + 1                               # check_array(ensure_min_samples=...)  quantile.py:205-210
+        if n < need or y.shape[0] < need:
+            raise ValueError(f'Found array with {min(n, y.shape[0])} sample(s) while a minimum of {need} is required.')
+        if y.shape != X.shape:
+            raise ValueError(f'X {tuple(X.shape)} and y {tuple(y.shape)} must have the same shape')
+        table = whole_series_table(n)
+        self._sx = engine.qm_fit(X, table, valid=valid, want_y_climo=False)
+        self._sy = engine.qm_fit(y, table, valid=valid, want_y_climo=False)
+        self._sy.nonfinite = self._sx.nonfinite                       # one flag for the model
+        self._frame = engine.qmr_frame(self._sx, self._sy, _lib.EXTRAPOLATE[self.extrapolate], int(self.n_endpoints))
+        return self
+
+    def check_fit(self):
+        self._sx.check_finite()
+
+    def _ranks(self, X):
+        return None
+
+    def predict_batched(self, X: torch.Tensor):
+        if not hasattr(self, '_sx'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
+                                 "appropriate arguments before using this estimator.")
+        return engine.qmr_predict(self._kind, X, self._sx, self._sy, self._frame, _lib.EXTRAPOLATE[self.extrapolate],
+                                  self.extrapolate == '1to1', rank=self._ranks(X))
+
+    # ---- per-cell API of the reference (one series)
+    def fit(self, X, y, **kwargs):
+        dev = cuda_device()
+        x, _, _ = series_to_device(X, dev)
+        yt, _, _ = series_to_device(y, dev)
+        if x.shape[1] != 1:
+            raise ValueError(f'X should have up to 1 features, found {x.shape[1]}')     # utils.check_max_features
+        if yt.shape[1] != 1:
+            raise ValueError('y must be 1-dimensional')
+        if x.dtype != yt.dtype:
+            x, yt = x.to(torch.float64), yt.to(torch.float64)
+        self.fit_batched(x, yt)
+        self.check_fit()
+        self._X_cdf = self._y_cdf = True
+        return self
+
+    def predict(self, X, **kwargs):
+        x, _, _ = series_to_device(X, cuda_device())
+        if not hasattr(self, '_sx'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
+                                 "appropriate arguments before using this estimator.")
+        in_dtype = x.dtype
+        if x.dtype != self._sx.dtype:
+            x = x.to(self._sx.dtype)
+        out = self.predict_batched(x[:, :1].contiguous())
+        self._sx.check_finite()
+        return out[:, 0].to(in_dtype).cpu().numpy()                   # y_hat = np.full_like(X)  quantile.py:265
+
+
+class EquidistantCdfMatcher(QuantileMappingReressor):
+    """Equidistant CDF matching (quantile.py:556-636): quantile mapping that preserves the difference
+    or the ratio between the new and the training X at equal plotting positions.  ``max_ratio`` other
+    than None makes the reference raise (``np.min(ratio, max_ratio)``, quantile.py:624) and is rejected."""
+
+    def __init__(self, kind='difference', extrapolate=None, n_endpoints=10, max_ratio=None):
+        if kind not in ['difference', 'ratio']:
+            raise NotImplementedError('kind must be either difference or ratio')
+        self.kind = kind
+        self.extrapolate = extrapolate
+        self.n_endpoints = n_endpoints
+        self.max_ratio = max_ratio
+        if self.n_endpoints < 2:
+            raise ValueError('Invalid number of n_endpoints, must be >= 2')
+
+    @property
+    def _kind(self):
+        return _lib.QMR_EDCDF_DIFFERENCE if self.kind == 'difference' else _lib.QMR_EDCDF_RATIO
+
+    def _ranks(self, X):
+        if self.kind == 'ratio' and self.max_ratio is not None:
+            raise TypeError("'float' object cannot be interpreted as an integer")   # np.min(ratio, max_ratio)
+        # np.argsort position of every step inside its cell's series (quantile.py:607-609)
+        return engine.series_rank(X, whole_series_table(X.shape[0]), ordinal=True, valid=self._sx.valid,
+                                  nonfinite=self._sx.nonfinite)

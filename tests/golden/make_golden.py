@@ -132,6 +132,40 @@ def main():
     for tag, qt in QT_VARIANTS.items():
         qm_qt_case(tag, qt, 365, 1000, 2, 16)           # T_pred > T_fit: both tails are reached
 
+    # --- 2b. QuantileMappingReressor / EquidistantCdfMatcher, every extrapolate mode
+    QMR = ref['quantile'].QuantileMappingReressor
+    EDC = ref['quantile'].EquidistantCdfMatcher
+
+    def qmr_case(name, Tf, Tp, C, seed, dtype=np.float32, ne=7, offset=0.0):
+        Xtr, ytr, _ = synth.temperature(Tf, C, seed, dtype)
+        _, _, Xp = synth.temperature(Tp, C, seed + 100, dtype)
+        Xp = (Xp + dtype(offset)).astype(dtype)
+        arrays = dict(Xtr=Xtr, ytr=ytr, Xp=Xp, n_endpoints=np.int64(ne))
+        for ex in (None, 'min', 'max', 'both', '1to1'):
+            tag = 'none' if ex is None else ex
+            out = np.empty((Tp, C), dtype=dtype)
+            od, orat = np.empty((Tp, C), dtype=dtype), np.empty((Tp, C), dtype=dtype)
+            for c in range(C):
+                out[:, c] = QMR(extrapolate=ex, n_endpoints=ne).fit(Xtr[:, c:c + 1], ytr[:, c]).predict(Xp[:, c:c + 1])
+                od[:, c] = EDC(kind='difference', extrapolate=ex, n_endpoints=ne).fit(Xtr[:, c:c + 1], ytr[:, c]).predict(Xp[:, c:c + 1])
+                orat[:, c] = EDC(kind='ratio', extrapolate=ex, n_endpoints=ne).fit(Xtr[:, c:c + 1], ytr[:, c]).predict(Xp[:, c:c + 1])
+            arrays[f'qmr_{tag}'], arrays[f'diff_{tag}'], arrays[f'ratio_{tag}'] = out, od, orat
+        save(name, **arrays)
+
+    qmr_case('qmr_equal_len', 730, 730, 3, 17)
+    qmr_case('qmr_pred_longer_shifted', 500, 1200, 2, 18, offset=1.5)      # values beyond both ends of the fitted range
+    qmr_case('qmr_f64_shorter', 900, 400, 2, 19, dtype=np.float64, ne=10)
+
+    # the reference's own known-answer test (test_pointwise_models.py:323-344)
+    xs = np.arange(1, 22)
+    ka = {}
+    for kind in ('difference', 'ratio'):
+        Xt = xs + 2 if kind == 'difference' else xs * 2
+        got = EDC(kind=kind).fit(pd.DataFrame(xs), pd.DataFrame(xs + 3)).predict(pd.DataFrame(Xt))
+        assert (got.reshape(-1, 1) == ((xs + 3) + 2 if kind == 'difference' else (xs + 3) * 2).reshape(-1, 1)).all()
+        ka[kind] = got
+    save('edcdf_known_answer', x=xs, **ka)
+
     qm_case('qm_equal_len', 730, 730, 3, 10)
     qm_case('qm_pred_longer', 365, 1000, 3, 11)      # exercises both OLS tails
     qm_case('qm_pred_shorter', 1000, 300, 3, 12)

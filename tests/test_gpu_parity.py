@@ -172,6 +172,59 @@ def _expected_rank_map(x, y):
     return torch.gather(ys, 0, r - 1)
 
 
+# ------------------------------------------------------------------ QuantileMappingReressor / EquidistantCdfMatcher
+@pytest.mark.parametrize('name', ['qmr_equal_len', 'qmr_pred_longer_shifted', 'qmr_f64_shorter'])
+@pytest.mark.parametrize('ex', [None, 'min', 'max', 'both', '1to1'])
+def test_qm_regressor_and_edcdf_golden(dev, golden, name, ex):
+    """quantile.py:160-395, 556-636 for every extrapolate mode, against the live-reference vectors:
+    1e-5 relative (values are float32 / float64 like the reference's) on every step the reference
+    itself resolves (oracle.qmr_well_conditioned); the rest must merely be produced."""
+    g = golden(name)
+    ne, tag = int(g['n_endpoints']), ('none' if ex is None else ex)
+    scale = np.std(g['ytr'])
+    models = {'qmr': pm().QuantileMappingReressor(extrapolate=ex, n_endpoints=ne),
+              'diff': pm().EquidistantCdfMatcher(kind='difference', extrapolate=ex, n_endpoints=ne),
+              'ratio': pm().EquidistantCdfMatcher(kind='ratio', extrapolate=ex, n_endpoints=ne)}
+    for key, model in models.items():
+        pw = pm().PointWiseDownscaler(model)
+        pw.fit(g['Xtr'], g['ytr'])
+        got = pw.predict(g['Xp'])
+        assert got.dtype == g['Xp'].dtype and got.shape == g['Xp'].shape
+        for c in range(g['Xp'].shape[1]):
+            st = oracle.qm_regressor_fit(g['Xtr'][:, c], g['ytr'][:, c], ex, ne)
+            ok = oracle.qmr_well_conditioned(st, g['Xp'][:, c], 'regressor' if key == 'qmr' else 'edcdf')
+            assert ok.sum() > 0.5 * len(ok)
+            assert_close(got[ok, c], g[f'{key}_{tag}'][ok, c], scale=scale)
+    # per-cell estimator API of the reference
+    m = pm().QuantileMappingReressor(extrapolate=ex, n_endpoints=ne).fit(g['Xtr'][:, :1], g['ytr'][:, 0])
+    o = m.predict(g['Xp'][:, :1])
+    st = oracle.qm_regressor_fit(g['Xtr'][:, 0], g['ytr'][:, 0], ex, ne)
+    ok = oracle.qmr_well_conditioned(st, g['Xp'][:, 0], 'regressor')
+    assert o.shape == (len(g['Xp']),) and o.dtype == g['Xp'].dtype
+    assert_close(o[ok], g[f'qmr_{tag}'][ok, 0], scale=scale)
+
+
+def test_edcdf_known_answer(dev, golden):
+    """The reference's own exact test (test_pointwise_models.py:323-344)."""
+    x = golden('edcdf_known_answer')['x']
+    for kind, Xt, want in (('difference', x + 2, (x + 3) + 2), ('ratio', x * 2, (x + 3) * 2)):
+        m = pm().EquidistantCdfMatcher(kind=kind).fit(pd.DataFrame(x), pd.DataFrame(x + 3))
+        got = m.predict(pd.DataFrame(Xt))
+        assert (got.reshape(-1, 1) == want.reshape(-1, 1)).all()
+
+
+def test_qm_regressor_errors(dev):
+    with pytest.raises(ValueError, match='n_endpoints'):
+        pm().QuantileMappingReressor(n_endpoints=1)
+    with pytest.raises(NotImplementedError):
+        pm().EquidistantCdfMatcher(kind='sum')
+    x = np.arange(15.0).reshape(-1, 1)
+    with pytest.raises(ValueError, match='minimum of 21'):
+        pm().QuantileMappingReressor().fit(x, x[:, 0])                 # 2 * n_endpoints + 1 samples needed
+    with pytest.raises(ValueError, match='extrapolate'):
+        pm().QuantileMappingReressor(extrapolate='sideways').fit(np.arange(30.0).reshape(-1, 1), np.arange(30.0))
+
+
 # ------------------------------------------------------------------ BCSD
 @pytest.mark.parametrize('name,kw', [
     ('bcsd_t_month_anoms', {}),

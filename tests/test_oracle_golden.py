@@ -189,3 +189,42 @@ def test_analog_regression_thresh_one_class():
     Xtr, ytr, Xq = synth.analog(200, 20, 1, 3, seed=3)
     with pytest.raises(ValueError, match='at least 2 classes'):
         oracle.analog_regression_predict(Xtr[..., 0], ytr[:, 0], Xq[..., 0], 5, thresh=1e6)
+
+
+# ------------------------------------------------------------------ QuantileMappingReressor / EquidistantCdfMatcher
+EX_MODES = [None, 'min', 'max', 'both', '1to1']
+
+
+@pytest.mark.parametrize('name', ['qmr_equal_len', 'qmr_pred_longer_shifted', 'qmr_f64_shorter'])
+def test_qm_regressor_and_edcdf(golden, name):
+    """quantile.py:160-395, 556-636 against the live-reference vectors, every extrapolate mode.
+    Steps that reach the reference's synthetic +-1e20 CDF points are excluded (no significant digits
+    in the reference itself, see oracle.qmr_well_conditioned); everything else is bit-exact."""
+    g = golden(name)
+    ne = int(g['n_endpoints'])
+    for ex in EX_MODES:
+        tag = 'none' if ex is None else ex
+        n_checked = 0
+        for c in range(g['Xp'].shape[1]):
+            st = oracle.qm_regressor_fit(g['Xtr'][:, c], g['ytr'][:, c], ex, ne)
+            x = g['Xp'][:, c]
+            o = oracle.qm_regressor_predict(st, x)
+            assert o.dtype == x.dtype
+            ok = oracle.qmr_well_conditioned(st, x, 'regressor')
+            np.testing.assert_array_equal(o[ok], g[f'qmr_{tag}'][ok, c])
+            n_checked += ok.sum()
+            ok = oracle.qmr_well_conditioned(st, x, 'edcdf')
+            for kind in ('difference', 'ratio'):
+                o = oracle.edcdf_predict(st, x, kind)
+                np.testing.assert_array_equal(o[ok], g[f"{'diff' if kind == 'difference' else 'ratio'}_{tag}"][ok, c])
+        assert n_checked > 0.5 * g['Xp'].size
+
+
+def test_edcdf_known_answer(golden):
+    """The reference's own test (test_pointwise_models.py:323-344): exact equality."""
+    g = golden('edcdf_known_answer')
+    x = g['x']
+    st = oracle.qm_regressor_fit(x, x + 3)
+    assert (oracle.edcdf_predict(st, x + 2, 'difference') == (x + 3) + 2).all()
+    assert (oracle.edcdf_predict(st, x * 2, 'ratio') == (x + 3) * 2).all()
+    assert (g['difference'] == (x + 3) + 2).all() and (g['ratio'] == (x + 3) * 2).all()
