@@ -232,6 +232,43 @@ int sdb_qmr_predict(int kind, const void* X, int dtype, int64_t ld, int64_t n_ce
                     void* out, int out_dtype, int64_t ld_out,
                     const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
 
+/*
+ * Detrending quantile map (QuantileMapper(detrend=True), quantile.py:94-98,127-145; per time group
+ * through BcsdBase(qm_kwargs={'detrend': True})) — SURVEY.md §8(f) row 2.  The mapper itself is
+ * sdb_qm_fit / sdb_qm_predict on float64 residuals; these entry points are the steps around it.
+ */
+#define SDB_TREND_REMOVE  0   /* out = v - (j * slope + intercept)                          trend.py:54-64   */
+#define SDB_TREND_RESTORE 1   /* out = (v + (j * slope + intercept)) - (intercept - intercept_ref)   trend.py:66-77, quantile.py:143-145 */
+
+/* LinearTrendTransformer.fit for every (cell, group): least-squares line of the group's series (time
+ * order) on its positions 0..len-1, float64.  slope / intercept: [n_groups, ld_out].   trend.py:40-52 */
+int sdb_group_trend(const void* v, int dtype, int64_t ld, int64_t n_cells,
+                    const int32_t* rows, const int32_t* len, int n_groups, int max_len,
+                    double* slope, double* intercept, int64_t ld_out,
+                    const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+/* Remove / restore the lines of sdb_group_trend; j = position of the step inside its group.
+ * intercept_ref (RESTORE): the intercepts found at FIT time, indexed like slope / intercept. */
+int sdb_trend_apply(int mode, const void* v, int dtype, int64_t ld, int64_t n_cells,
+                    const int32_t* rows, const int32_t* len, int n_groups, int max_len,
+                    const double* slope, const double* intercept, const double* intercept_ref, int64_t ld_coef,
+                    double* out, int64_t ld_out, const uint8_t* cell_valid, void* stream);
+
+/* BcsdTemperature.predict up to the mapper (bcsd.py:247-256): shift = centred 9-sample mean of the
+ * climate-trend group - x_climo, key = X - shift, both float64 [T, ld_out].  roll_nbr as in sdb_qm_predict. */
+int sdb_bcsd_shift(const void* X, int dtype, int64_t ld, int64_t n_cells,
+                   const int32_t* rows, const int32_t* len, const int32_t* state_gid, int n_groups, int max_len,
+                   const int32_t* roll_nbr, const void* x_climo, int64_t ld_climo,
+                   double* shift, double* key, int64_t ld_out,
+                   const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+/* ... and after it (bcsd.py:263-269, 170-185): BCSD_T out = shift + mapped [- y_climo];
+ * BCSD_P out = mapped [/ y_climo]; QM out = mapped.  mapped / shift: float64 [T, ld_in]. */
+int sdb_bcsd_combine(int mode, const double* mapped, const double* shift, int64_t ld_in, int64_t n_cells,
+                     const int32_t* rows, const int32_t* len, const int32_t* state_gid, int n_groups, int max_len,
+                     const void* y_climo, int climo_dtype, int64_t ld_climo, int return_anoms,
+                     void* out, int out_dtype, int64_t ld_out, const uint8_t* cell_valid, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,8 +34,11 @@ from .quantile import (  # noqa: F401
     qm_regressor_fit,
     qm_regressor_predict,
     qmr_well_conditioned,
+    linear_trend_fit,
     quantile_mapper_fit,
+    quantile_mapper_fit_detrend,
     quantile_mapper_transform,
+    quantile_mapper_transform_detrend,
     rank_max_ties,
 )
 from .bcsd import (  # noqa: F401

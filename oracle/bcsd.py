@@ -12,7 +12,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from .quantile import quantile_mapper_fit, quantile_mapper_transform
+from .quantile import (quantile_mapper_fit, quantile_mapper_fit_detrend, quantile_mapper_transform,
+                       quantile_mapper_transform_detrend)
 
 
 def _group_mean_like_pandas(v: np.ndarray, how: str = 'groupby') -> np.generic:
@@ -44,6 +45,14 @@ def _group_mean_like_pandas(v: np.ndarray, how: str = 'groupby') -> np.generic:
     return ft(s / ft(len(v)))
 
 
+def _map_group(x, fitted, qt):
+    """One group through its fitted QuantileMapper (bcsd.py:69-79): plain, or — when the group was
+    fitted with detrend=True (a dict) — the detrending transform."""
+    if isinstance(fitted, dict):
+        return quantile_mapper_transform_detrend(x, fitted, return_rank=True, **(qt or {}))
+    return quantile_mapper_transform(x, fitted, return_rank=True, **(qt or {}))
+
+
 def rolling9_centered(x: np.ndarray) -> np.ndarray:
     """``x.rolling(9, center=True, min_periods=1).mean()`` (bcsd.py:247-248) on one
     time-ordered group subsequence; float64 result."""
@@ -60,7 +69,8 @@ def rolling9_centered(x: np.ndarray) -> np.ndarray:
     return tot / cnt
 
 
-def bcsd_temperature_fit(X: np.ndarray, y: np.ndarray, fit_groups, mean_how: str = 'groupby') -> dict:
+def bcsd_temperature_fit(X: np.ndarray, y: np.ndarray, fit_groups, mean_how: str = 'groupby',
+                         detrend: bool = False) -> dict:
     """BcsdTemperature.fit (bcsd.py:197-228): per group x/y climatology + sorted y."""
     X = np.asarray(X).reshape(-1)
     y = np.asarray(y).reshape(-1)
@@ -68,7 +78,9 @@ def bcsd_temperature_fit(X: np.ndarray, y: np.ndarray, fit_groups, mean_how: str
     for key, rows in fit_groups:
         st['x_climo'][key] = _group_mean_like_pandas(X[rows], mean_how)       # bcsd.py:222
         st['y_climo'][key] = _group_mean_like_pandas(y[rows], mean_how)       # bcsd.py:223
-        st['sorted'][key] = quantile_mapper_fit(y[rows])            # bcsd.py:226 → quantile.py:462
+        # bcsd.py:226 → quantile.py:462 (qm_kwargs detrend=True: the mapper of each group detrends the
+        # group's own subsequence, positions 0..len-1, quantile.py:94-98)
+        st['sorted'][key] = quantile_mapper_fit_detrend(y[rows]) if detrend else quantile_mapper_fit(y[rows])
     return st
 
 
@@ -93,8 +105,7 @@ def bcsd_temperature_predict(st: dict, X: np.ndarray, roll_groups, qm_groups,
     xqm = np.empty(T, dtype=np.float64)
     ranks = np.empty(T, dtype=np.int64)
     for key, rows in qm_groups:                                      # bcsd.py:260, 69-79
-        xqm[rows], ranks[rows] = quantile_mapper_transform(no_shift[rows], st['sorted'][key],
-                                                           return_rank=True, **(qt or {}))
+        xqm[rows], ranks[rows] = _map_group(no_shift[rows], st['sorted'][key], qt)
     out = shift + xqm                                                # bcsd.py:263
     if return_anoms:                                                 # bcsd.py:266-267
         for key, rows in qm_groups:
@@ -103,7 +114,7 @@ def bcsd_temperature_predict(st: dict, X: np.ndarray, roll_groups, qm_groups,
 
 
 def bcsd_precipitation_fit(y: np.ndarray, fit_groups, return_anoms: bool = True,
-                           mean_how: str = 'groupby') -> dict:
+                           mean_how: str = 'groupby', detrend: bool = False) -> dict:
     """BcsdPrecipitation.fit (bcsd.py:115-147).  X_train is validated only, never used."""
     y = np.asarray(y).reshape(-1)
     st = {'y_climo': {}, 'sorted': {}}
@@ -112,7 +123,7 @@ def bcsd_precipitation_fit(y: np.ndarray, fit_groups, return_anoms: bool = True,
     if return_anoms and min(float(v) for v in st['y_climo'].values()) <= 0:   # bcsd.py:140-141
         raise ValueError('Invalid value in target climatology')
     for key, rows in fit_groups:
-        st['sorted'][key] = quantile_mapper_fit(y[rows])            # bcsd.py:145
+        st['sorted'][key] = quantile_mapper_fit_detrend(y[rows]) if detrend else quantile_mapper_fit(y[rows])  # bcsd.py:145
     return st
 
 
@@ -123,8 +134,7 @@ def bcsd_precipitation_predict(st: dict, X: np.ndarray, qm_groups, return_anoms:
     out = np.empty(len(X), dtype=np.float64)
     ranks = np.empty(len(X), dtype=np.int64)
     for key, rows in qm_groups:                                      # bcsd.py:167
-        out[rows], ranks[rows] = quantile_mapper_transform(X[rows], st['sorted'][key],
-                                                           return_rank=True, **(qt or {}))
+        out[rows], ranks[rows] = _map_group(X[rows], st['sorted'][key], qt)
     if return_anoms:                                                 # bcsd.py:170-185
         for key, rows in qm_groups:
             out[rows] = out[rows] / np.float64(st['y_climo'][key])

@@ -32,6 +32,40 @@ def quantile_mapper_fit(v: np.ndarray) -> np.ndarray:
     return np.sort(np.asarray(v).reshape(-1))
 
 
+def linear_trend_fit(v: np.ndarray) -> tuple[float, float]:
+    """LinearTrendTransformer.fit (trend.py:40-52): sklearn LinearRegression of the series on
+    ``arange(n)`` — centred least squares in float64.  Returns (slope, intercept)."""
+    y = np.asarray(v, dtype=np.float64).reshape(-1)
+    t = np.arange(len(y), dtype=np.float64)
+    tm, ym = t.mean(), y.mean()
+    dt = t - tm
+    stt = np.dot(dt, dt)
+    slope = float(np.dot(dt, y - ym) / stt) if stt > 0 else 0.0
+    return slope, float(ym - tm * slope)
+
+
+def quantile_mapper_fit_detrend(v: np.ndarray) -> dict:
+    """QuantileMapper(detrend=True).fit (quantile.py:94-105): remove the series' own linear trend
+    (float64: ``X - trendline``, trend.py:54-64,79-83), keep the sorted residuals and the fitted
+    intercept (needed by transform, quantile.py:145)."""
+    v = np.asarray(v).reshape(-1)
+    slope, icpt = linear_trend_fit(v)
+    resid = v - (np.arange(len(v)) * slope + icpt)
+    return {'sorted': np.sort(resid), 'intercept': icpt}
+
+
+def quantile_mapper_transform_detrend(x: np.ndarray, st: dict, return_rank: bool = False, **qt):
+    """QuantileMapper(detrend=True).transform (quantile.py:127-147): detrend the NEW data with its own
+    trend, map the residuals, add that trend back and move the baseline to the fitted intercept."""
+    x = np.asarray(x).reshape(-1)
+    slope, icpt = linear_trend_fit(x)
+    trend = np.arange(len(x)) * slope + icpt
+    mapped, r = quantile_mapper_transform(x - trend, st['sorted'], return_rank=True, **qt)
+    out = mapped + trend                                         # quantile.py:143  (inverse_transform)
+    out -= icpt - st['intercept']                                # quantile.py:145
+    return (out, r) if return_rank else out
+
+
 def _ols_line(x: np.ndarray, y: np.ndarray) -> tuple[float, float]:
     """Closed form of sklearn LinearRegression on one feature (used at quantile.py:532-543):
     centred least squares, returns (slope, intercept) in float64."""

@@ -58,14 +58,20 @@ def pointwise_fit_predict(spec: dict, X_train, y_train, X_pred, index_fit=None, 
         if not valid[c]:
             continue
         if name == 'QuantileMapper':
-            st = quantile.quantile_mapper_fit(np.asarray(y_train)[:, c])
-            res = quantile.quantile_mapper_transform(X_pred[:, c], st, **(spec.get('qt_kwargs') or {}))
+            if spec.get('detrend'):
+                st = quantile.quantile_mapper_fit_detrend(np.asarray(y_train)[:, c])
+                res = quantile.quantile_mapper_transform_detrend(X_pred[:, c], st, **(spec.get('qt_kwargs') or {}))
+            else:
+                st = quantile.quantile_mapper_fit(np.asarray(y_train)[:, c])
+                res = quantile.quantile_mapper_transform(X_pred[:, c], st, **(spec.get('qt_kwargs') or {}))
         elif name == 'BcsdTemperature':
-            st = bcsd.bcsd_temperature_fit(np.asarray(X_train)[:, c], np.asarray(y_train)[:, c], fit_groups, how)
+            st = bcsd.bcsd_temperature_fit(np.asarray(X_train)[:, c], np.asarray(y_train)[:, c], fit_groups, how,
+                                           detrend=bool(spec.get('detrend')))
             res = bcsd.bcsd_temperature_predict(st, X_pred[:, c], roll_groups, qm_groups, anoms,
                                                 qt=spec.get('qt_kwargs'))
         elif name == 'BcsdPrecipitation':
-            st = bcsd.bcsd_precipitation_fit(np.asarray(y_train)[:, c], fit_groups, anoms, how)
+            st = bcsd.bcsd_precipitation_fit(np.asarray(y_train)[:, c], fit_groups, anoms, how,
+                                             detrend=bool(spec.get('detrend')))
             res = bcsd.bcsd_precipitation_predict(st, X_pred[:, c], qm_groups, anoms, qt=spec.get('qt_kwargs'))
         elif name == 'PureAnalog':
             res = gard.pure_analog_predict(np.asarray(X_train)[:, :, c], np.asarray(y_train)[:, c],

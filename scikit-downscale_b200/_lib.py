@@ -24,6 +24,7 @@ class CunnaneOpts(ctypes.Structure):
     _fields_ = [('alpha', c_double), ('beta', c_double), ('n_endpoints', ctypes.c_int32), ('extrapolate', ctypes.c_int32)]
 
 
+TREND_REMOVE, TREND_RESTORE = 0, 1
 QMR_REGRESSOR, QMR_EDCDF_DIFFERENCE, QMR_EDCDF_RATIO = 0, 1, 2
 ANALOG_BEST, ANALOG_SAMPLE, ANALOG_WEIGHT, ANALOG_MEAN, ANALOG_REGRESSION = 0, 1, 2, 3, 4
 
@@ -62,6 +63,14 @@ SIGNATURES = {
                                 c_void_p, c_int64,
                                 c_void_p, c_int, c_int64,
                                 c_void_p, c_void_p, c_void_p]),
+    'sdb_group_trend': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
+                                c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'sdb_trend_apply': (c_int, [c_int, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    'sdb_bcsd_shift': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                               c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'sdb_bcsd_combine': (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                 c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

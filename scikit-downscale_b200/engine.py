@@ -348,3 +348,88 @@ def qmr_predict(kind: int, X: torch.Tensor, sx: QMFitted, sy: QMFitted, frame: t
                                    _ptr(rank), C, _ptr(out), _code(X), C, _ptr(sx.valid), _ptr(sx.nonfinite), _stream()),
                'sdb_qmr_predict')
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Detrending quantile map (QuantileMapper(detrend=True), quantile.py:94-98, 127-145)
+# ---------------------------------------------------------------------------------------------
+def group_trend(v: torch.Tensor, table: GroupTable, valid=None, nonfinite=None):
+    """LinearTrendTransformer.fit of every (cell, group) → (slope, intercept) float64 ``[G, C]``."""
+    lib = _lib.load()
+    ld = _check_2d(v, 'v')
+    T, C = v.shape
+    rows, length = table.device(v.device)
+    slope = torch.empty((table.n_groups, C), dtype=torch.float64, device=v.device)
+    icpt = torch.empty_like(slope)
+    _lib.check(lib.sdb_group_trend(_ptr(v), _code(v), ld, C, _ptr(rows), _ptr(length), table.n_groups,
+                                   table.rows.shape[1], _ptr(slope), _ptr(icpt), C, _ptr(valid), _ptr(nonfinite),
+                                   _stream()), 'sdb_group_trend')
+    return slope, icpt
+
+
+def trend_apply(mode: int, v: torch.Tensor, table: GroupTable, slope, icpt, icpt_ref=None, valid=None) -> torch.Tensor:
+    """Remove (``_lib.TREND_REMOVE``) or restore (``_lib.TREND_RESTORE``) the group trend lines → float64."""
+    lib = _lib.load()
+    ld = _check_2d(v, 'v')
+    T, C = v.shape
+    rows, length = table.device(v.device)
+    out = torch.empty((T, C), dtype=torch.float64, device=v.device)
+    _lib.check(lib.sdb_trend_apply(mode, _ptr(v), _code(v), ld, C, _ptr(rows), _ptr(length), table.n_groups,
+                                   table.rows.shape[1], _ptr(slope), _ptr(icpt), _ptr(icpt_ref), C, _ptr(out), C,
+                                   _ptr(valid), _stream()), 'sdb_trend_apply')
+    return out
+
+
+def _fit_gids(st: QMFitted, table: GroupTable, device) -> torch.Tensor:
+    try:
+        gid = np.array([st.sort_table.key_to_gid[k] for k in table.keys], dtype=np.int32)
+    except KeyError as e:
+        raise KeyError(e.args[0]) from None
+    return torch.from_numpy(gid).to(device)
+
+
+def _climo_by_sort(st: QMFitted, device):
+    x_climo, y_climo = st.x_climo, st.y_climo
+    if st.mean_table is not st.sort_table and (x_climo is not None or y_climo is not None):
+        sel = torch.as_tensor([st.mean_table.key_to_gid[k] for k in st.sort_table.keys], device=device)
+        x_climo = None if x_climo is None else x_climo.index_select(0, sel).contiguous()
+        y_climo = None if y_climo is None else y_climo.index_select(0, sel).contiguous()
+    return x_climo, y_climo
+
+
+def qm_predict_detrended(st_raw: QMFitted, st_res: QMFitted, icpt_fit: torch.Tensor, X: torch.Tensor, table: GroupTable,
+                         mode: int, *, return_anoms: bool = False, roll_nbr=None, out_dtype=None, cunnane=None):
+    """predict with detrending mappers: (shift →) remove the new data's trend → map the residuals through
+    the fitted residual CDFs → restore the trend at the fitted baseline (→ combine).  ``st_raw`` holds the
+    climatologies (and the mask), ``st_res`` the sorted float64 residuals, ``icpt_fit`` the fitted
+    intercepts ``[fitted group, C]``."""
+    lib = _lib.load()
+    ld = _check_2d(X, 'X')
+    T, C = X.shape
+    dev = X.device
+    rows, length = table.device(dev)
+    gid = _fit_gids(st_res, table, dev)
+    x_climo, y_climo = _climo_by_sort(st_raw, dev)
+    valid, flag = st_raw.valid, st_raw.nonfinite
+    shift = None
+    key = X
+    if mode == _lib.MODE_BCSD_T:
+        shift = torch.empty((T, C), dtype=torch.float64, device=dev)
+        key = torch.empty((T, C), dtype=torch.float64, device=dev)
+        nbr_dev = None if roll_nbr is None else torch.from_numpy(np.ascontiguousarray(roll_nbr, dtype=np.int32)).to(dev)
+        _lib.check(lib.sdb_bcsd_shift(_ptr(X), _code(X), ld, C, _ptr(rows), _ptr(length), _ptr(gid), table.n_groups,
+                                      table.rows.shape[1], _ptr(nbr_dev), _ptr(x_climo), C, _ptr(shift), _ptr(key), C,
+                                      _ptr(valid), _ptr(flag), _stream()), 'sdb_bcsd_shift')
+    slope, icpt = group_trend(key, table, valid, flag)
+    resid = trend_apply(_lib.TREND_REMOVE, key, table, slope, icpt, valid=valid)
+    mapped = qm_predict(st_res, resid, table, _lib.MODE_QM, out_dtype=torch.float64, cunnane=cunnane)
+    icpt_ref = icpt_fit.index_select(0, gid.long()).contiguous()
+    restored = trend_apply(_lib.TREND_RESTORE, mapped, table, slope, icpt, icpt_ref, valid=valid)
+    od = out_dtype or X.dtype
+    out = torch.empty((T, C), dtype=od, device=dev)
+    climo = y_climo if (return_anoms and mode != _lib.MODE_QM) else None
+    _lib.check(lib.sdb_bcsd_combine(mode, _ptr(restored), _ptr(shift), C, C, _ptr(rows), _ptr(length), _ptr(gid),
+                                    table.n_groups, table.rows.shape[1], _ptr(climo),
+                                    _code(climo) if climo is not None else _lib.SDB_F32, C, int(bool(return_anoms)),
+                                    _ptr(out), _TORCH_CODE[od], C, _ptr(valid), _stream()), 'sdb_bcsd_combine')
+    return out

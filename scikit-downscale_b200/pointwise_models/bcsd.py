@@ -13,7 +13,7 @@ from .. import _lib, engine
 from .base import TimeSynchronousDownscaler, cuda_device, series_to_device
 from .groupers import (DAY_GROUPER, MONTH_GROUPER, PaddedDOYGrouper, grouper_keys, groups_from_keys,
                        padded_doy_groups, rolling_neighbours)
-from .quantile import check_qt_kwargs, cunnane_opts
+from .quantile import check_lt_kwargs, check_qt_kwargs, cunnane_opts, fit_detrended
 from .utils import default_none_kwargs
 
 
@@ -52,9 +52,11 @@ class BcsdBase(TimeSynchronousDownscaler):
         for k in qm:
             if k not in ('detrend', 'lt_kwargs', 'qt_kwargs'):
                 raise TypeError(f"QuantileMapper.__init__() got an unexpected keyword argument '{k}'")
-        if qm.get('detrend', False):
-            raise NotImplementedError('qm_kwargs detrend=True is not on the B200 path yet')
+        self._detrend = bool(qm.get('detrend', False))
+        if self._detrend and self.timestep == 'daily':
+            raise NotImplementedError("qm_kwargs detrend=True with 'daily_nasa-nex' is not on the B200 path")
         check_qt_kwargs(qm.get('qt_kwargs'))
+        check_lt_kwargs(qm.get('lt_kwargs'))
 
     def _cunnane(self):
         """qm_kwargs['qt_kwargs'] → CunnaneTransformer settings of every group's mapper (bcsd.py:65-67)."""
@@ -91,6 +93,10 @@ class BcsdBase(TimeSynchronousDownscaler):
         sort_t, mean_t, how = self._fit_tables(index)
         self._state = engine.qm_fit(y, sort_t, valid=valid, X=X if self._needs_x_climo else None,
                                     mean_table=mean_t, mean_how=how)
+        if self._detrend:
+            # bcsd.py:65-67 with QuantileMapper(detrend=True): every group's mapper is fitted on the group's
+            # residuals about its own trend line (positions 0..len-1 of the group's subsequence)
+            self._state_res, self._icpt_fit = fit_detrended(y, sort_t, valid)
         self.n_features_in_ = 1
         return self
 
@@ -108,6 +114,16 @@ class BcsdBase(TimeSynchronousDownscaler):
             # different shape and the reference raises
             raise ValueError('shape of climo is not equal to input array')
         table, nbr = self._predict_tables(index)
+        if getattr(self, '_detrend', False):
+            if want_rank:
+                raise NotImplementedError('rank instrumentation is not available with detrend=True')
+            res = engine.qm_predict_detrended(self._state, self._state_res, self._icpt_fit, X, table, self._mode,
+                                              return_anoms=self.return_anoms, roll_nbr=nbr, out_dtype=out_dtype,
+                                              cunnane=self._cunnane())
+            if out is not None:
+                out.copy_(res)
+                return out
+            return res
         return engine.qm_predict(self._state, X, table, self._mode, return_anoms=self.return_anoms,
                                  roll_nbr=nbr, out_dtype=out_dtype, want_rank=want_rank, out=out,
                                  cunnane=self._cunnane())
@@ -126,10 +142,16 @@ class BcsdBase(TimeSynchronousDownscaler):
     def _spans(n_cells, chunk):
         return [(c0, min(c0 + chunk, n_cells)) for c0 in range(0, n_cells, chunk)]
 
+    def _no_detrend_streaming(self):
+        if bool(default_none_kwargs(self.qm_kwargs).get('detrend', False)):
+            raise NotImplementedError('the host-streaming path does not cover qm_kwargs detrend=True; '
+                                      'pass device tensors (or fewer cells than chunk_cells)')
+
     def fit_host(self, X, y, index, device=None, chunk_cells: int = 16384):
         """fit from HOST arrays ``[T, C]``: cell chunks travel host → device on a copy stream
         (strided 2-D DMA, pinned memory recommended) while the previous chunk is being fitted;
         the fitted state of all cells stays on the device."""
+        self._no_detrend_streaming()
         dev = cuda_device(device)
         Xh, yh = self._host2d(X, 'X'), self._host2d(y, 'y')
         if Xh.shape != yh.shape:

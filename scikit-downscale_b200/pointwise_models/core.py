@@ -190,6 +190,8 @@ class PointWiseDownscaler:
         """Host-resident BCSD block big enough to be worth the chunked copy/compute pipeline."""
         if not isinstance(self._model, BcsdBase) or blk.kind == 'xarray':
             return False
+        if (self._model.qm_kwargs or {}).get('detrend', False):
+            return False                                   # composed float64 path: whole block on the device
         d = blk.data
         on_host = (not isinstance(d, torch.Tensor)) or (not d.is_cuda)
         ok_dtype = (d.dtype in (torch.float32, torch.float64)) if isinstance(d, torch.Tensor) else (d.dtype in (np.float32, np.float64))

@@ -43,6 +43,30 @@ def check_qt_kwargs(qt_kwargs):
     cunnane_opts(qt_kwargs)
 
 
+def check_lt_kwargs(lt_kwargs):
+    """lt_kwargs → LinearTrendTransformer(**lt_kwargs) (quantile.py:96): only its own ``lr_kwargs``
+    argument exists (trend.py:31-32), and only settings that keep the plain least-squares line."""
+    for k, v in default_none_kwargs(lt_kwargs).items():
+        if k != 'lr_kwargs':
+            raise TypeError(f"LinearTrendTransformer.__init__() got an unexpected keyword argument '{k}'")
+        for kk, vv in default_none_kwargs(v).items():
+            if not ((kk == 'fit_intercept' and vv) or kk in ('copy_X', 'n_jobs', 'tol') or (kk == 'positive' and not vv)):
+                raise NotImplementedError(f'lr_kwargs {kk}={vv!r} is not supported on the B200 path')
+
+
+def fit_detrended(v: torch.Tensor, table, valid):
+    """Fit of detrending mappers for every (cell, group) of ``table`` (quantile.py:94-105): returns the
+    fitted state of the float64 residuals and the trend intercepts ``[group, C]`` (quantile.py:145 needs them)."""
+    flag = torch.zeros(1, dtype=torch.int32, device=v.device)
+    slope, icpt = engine.group_trend(v, table, valid, flag)
+    resid = engine.trend_apply(_lib.TREND_REMOVE, v, table, slope, icpt, valid=valid)
+    st = engine.qm_fit(resid, table, valid=valid, want_y_climo=False)
+    st.extra['raw_dtype'] = v.dtype
+    if int(flag.item()) != 0:
+        st.nonfinite.fill_(1)
+    return st, icpt
+
+
 def whole_series_table(n_rows: int) -> engine.GroupTable:
     return engine.GroupTable([(0, np.arange(n_rows))])
 
@@ -59,15 +83,24 @@ class QuantileMapper(TransformerMixin, BaseEstimator):
 
     # ---- batched (all cells) API used by PointWiseDownscaler
     def fit_batched(self, X: torch.Tensor, valid=None):
-        if self.detrend:
-            raise NotImplementedError('QuantileMapper(detrend=True) is not on the B200 path yet')
         check_qt_kwargs(self.qt_kwargs)
-        self._state = engine.qm_fit(X, whole_series_table(X.shape[0]), valid=valid, want_y_climo=False)
+        check_lt_kwargs(self.lt_kwargs)
+        table = whole_series_table(X.shape[0])
+        if self.detrend:
+            # quantile.py:94-98: the CDF is fitted on X minus its own linear trend (float64 residuals)
+            self._state, self._icpt_fit = fit_detrended(X, table, valid)
+        else:
+            self._state = engine.qm_fit(X, table, valid=valid, want_y_climo=False)
         return self
 
     def transform_batched(self, X: torch.Tensor, out_dtype=None, want_rank=False):
         if not hasattr(self, '_state'):
             raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet.")
+        if self.detrend:
+            if want_rank:
+                raise NotImplementedError('rank instrumentation is not available with detrend=True')
+            return engine.qm_predict_detrended(self._state, self._state, self._icpt_fit, X, whole_series_table(X.shape[0]),
+                                               _lib.MODE_QM, out_dtype=out_dtype, cunnane=cunnane_opts(self.qt_kwargs))
         return engine.qm_predict(self._state, X, whole_series_table(X.shape[0]), _lib.MODE_QM,
                                  out_dtype=out_dtype, want_rank=want_rank, cunnane=cunnane_opts(self.qt_kwargs))
 

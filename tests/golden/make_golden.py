@@ -166,6 +166,21 @@ def main():
         ka[kind] = got
     save('edcdf_known_answer', x=xs, **ka)
 
+    # --- 2c. detrending mappers: QuantileMapper(detrend=True), BCSD qm_kwargs detrend
+    def qm_detrend_case(name, Tf, Tp, C, seed, dtype=np.float32):
+        _, ytr, _ = synth.temperature(Tf, C, seed, dtype)
+        _, _, Xp = synth.temperature(Tp, C, seed + 100, dtype)
+        ytr = (ytr + np.linspace(0, 2, Tf)[:, None]).astype(dtype)         # give the series trends to remove
+        Xp = (Xp + np.linspace(-1, 3, Tp)[:, None]).astype(dtype)
+        out = np.empty((Tp, C), dtype=np.float64)
+        for c in range(C):
+            out[:, c] = QuantileMapper(detrend=True).fit(ytr[:, c:c + 1]).transform(Xp[:, c:c + 1])[:, 0]
+        save(name, ytr=ytr, Xp=Xp, out=out)
+
+    qm_detrend_case('qm_detrend_equal', 900, 900, 2, 26)
+    qm_detrend_case('qm_detrend_longer', 400, 1100, 2, 27)
+    qm_detrend_case('qm_detrend_f64', 500, 450, 2, 28, dtype=np.float64)
+
     qm_case('qm_equal_len', 730, 730, 3, 10)
     qm_case('qm_pred_longer', 365, 1000, 3, 11)      # exercises both OLS tails
     qm_case('qm_pred_shorter', 1000, 300, 3, 12)
@@ -199,6 +214,9 @@ def main():
     bcsd_t_case('bcsd_t_month_future', 1461, 2192, 3, 22, start_pred='1985-01-01')   # T_pred > T_fit → tails
     bcsd_t_case('bcsd_t_month_future_qt', 1096, 1826, 2, 25, start_pred='1984-01-01',
                 qm_kwargs={'qt_kwargs': dict(alpha=0.3, beta=0.5, n_endpoints=5, extrapolate='max')})
+    bcsd_t_case('bcsd_t_month_detrend', 1461, 1461, 3, 29, nan_cells=(1,), qm_kwargs={'detrend': True})
+    bcsd_t_case('bcsd_t_month_detrend_future', 1096, 1826, 2, 31, start_pred='1984-01-01', return_anoms=False,
+                qm_kwargs={'detrend': True})
     bcsd_t_case('bcsd_t_month_f64', 1096, 1096, 2, 23, dtype=np.float64)
     bcsd_t_case('bcsd_t_month_30yr', 10950, 10950, 1, 0)                              # BASELINE config[0]
     bcsd_t_case('bcsd_t_nasanex', 1096, 1096, 2, 24, start_fit='1980-01-01',
@@ -218,6 +236,7 @@ def main():
         save(name, Xtr=Xtr, ytr=ytr, Xp=Xp, out=out, out64=out64,
              start_fit=np.array(start_fit), start_pred=np.array(start_pred or start_fit))
 
+    bcsd_p_case('bcsd_p_month_detrend', 1461, 1461, 2, 32, qm_kwargs={'detrend': True})
     bcsd_p_case('bcsd_p_month_anoms', 1461, 1461, 3, 30)
     bcsd_p_case('bcsd_p_month_abs_future', 1096, 1461, 3, 31, start_pred='1984-01-01', return_anoms=False)
     bcsd_p_case('bcsd_p_nasanex', 1096, 1096, 2, 32, start_fit='1980-01-01',

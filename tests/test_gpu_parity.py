@@ -172,6 +172,20 @@ def _expected_rank_map(x, y):
     return torch.gather(ys, 0, r - 1)
 
 
+@pytest.mark.parametrize('name', ['qm_detrend_equal', 'qm_detrend_longer', 'qm_detrend_f64'])
+def test_qm_detrend_golden(dev, golden, name):
+    """QuantileMapper(detrend=True) (quantile.py:94-98, 127-145) against the live-reference vectors."""
+    g = golden(name)
+    pw = pm().PointWiseDownscaler(pm().QuantileMapper(detrend=True))
+    pw.fit(g['ytr'])
+    got = pw.transform(g['Xp'])
+    assert got.dtype == g['Xp'].dtype
+    assert_close(got, g['out'].astype(g['Xp'].dtype), scale=np.std(g['ytr']))
+    for c in range(g['Xp'].shape[1]):                             # per-cell API: float64 like the reference
+        o = pm().QuantileMapper(detrend=True).fit(g['ytr'][:, c:c + 1]).transform(g['Xp'][:, c:c + 1])[:, 0]
+        np.testing.assert_allclose(o, g['out'][:, c], rtol=1e-9, atol=1e-9)
+
+
 # ------------------------------------------------------------------ QuantileMappingReressor / EquidistantCdfMatcher
 @pytest.mark.parametrize('name', ['qmr_equal_len', 'qmr_pred_longer_shifted', 'qmr_f64_shorter'])
 @pytest.mark.parametrize('ex', [None, 'min', 'max', 'both', '1to1'])
@@ -231,6 +245,8 @@ def test_qm_regressor_errors(dev):
     ('bcsd_t_month_abs', {'return_anoms': False}),
     ('bcsd_t_month_future', {}),
     ('bcsd_t_month_future_qt', {'qm_kwargs': {'qt_kwargs': dict(alpha=0.3, beta=0.5, n_endpoints=5, extrapolate='max')}}),
+    ('bcsd_t_month_detrend', {'qm_kwargs': {'detrend': True}}),
+    ('bcsd_t_month_detrend_future', {'qm_kwargs': {'detrend': True}, 'return_anoms': False}),
     ('bcsd_t_month_f64', {}),
     ('bcsd_t_month_30yr', {}),
     ('bcsd_t_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
@@ -262,6 +278,7 @@ def test_bcsd_temperature_golden(dev, golden, name, kw):
 
 @pytest.mark.parametrize('name,kw', [
     ('bcsd_p_month_anoms', {}),
+    ('bcsd_p_month_detrend', {'qm_kwargs': {'detrend': True}}),
     ('bcsd_p_month_abs_future', {'return_anoms': False}),
     ('bcsd_p_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
 ])

@@ -110,4 +110,6 @@ def test_estimator_surface_and_no_cpu_fallback():
     m._pre_fit()
     assert issubclass(m.time_grouper, PaddedDOYGrouper)
     with pytest.raises(NotImplementedError):
-        QuantileMapper(detrend=True).fit_batched(None)
+        BcsdTemperature(time_grouper='daily_nasa-nex', qm_kwargs={'detrend': True})._pre_fit()
+    with pytest.raises(TypeError):
+        QuantileMapper(qt_kwargs={'gamma': 1}).fit_batched(None)       # CunnaneTransformer has no such argument

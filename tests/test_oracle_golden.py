@@ -80,6 +80,8 @@ def test_padded_doy_grouper(golden):
     ('bcsd_t_month_abs', {'return_anoms': False}),
     ('bcsd_t_month_future', {}),
     ('bcsd_t_month_future_qt', {'qt_kwargs': dict(alpha=0.3, beta=0.5, n_endpoints=5, extrapolate='max')}),
+    ('bcsd_t_month_detrend', {'detrend': True}),
+    ('bcsd_t_month_detrend_future', {'detrend': True, 'return_anoms': False}),
     ('bcsd_t_month_f64', {}),
     ('bcsd_t_month_30yr', {}),
     ('bcsd_t_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
@@ -101,7 +103,8 @@ def test_bcsd_temperature(golden, name, kw):
             assert np.isnan(out[:, c]).all() and np.isnan(g['out'][:, c]).all()
             continue
         how = 'frame' if spec['time_grouper'] == 'daily_nasa-nex' else 'groupby'
-        st = oracle.bcsd_temperature_fit(g['Xtr'][:, c], g['ytr'][:, c], fit_groups, how)
+        st = oracle.bcsd_temperature_fit(g['Xtr'][:, c], g['ytr'][:, c], fit_groups, how,
+                                         detrend=kw.get('detrend', False))
         o = oracle.bcsd_temperature_predict(st, g['Xp'][:, c], roll_groups, qm_groups,
                                             kw.get('return_anoms', True), qt=kw.get('qt_kwargs'))
         _close(o, ref[:, c], rtol=0, atol=2e-12 * max(1.0, scale))
@@ -109,6 +112,7 @@ def test_bcsd_temperature(golden, name, kw):
 
 @pytest.mark.parametrize('name,kw', [
     ('bcsd_p_month_anoms', {}),
+    ('bcsd_p_month_detrend', {'detrend': True}),
     ('bcsd_p_month_abs_future', {'return_anoms': False}),
     ('bcsd_p_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
 ])
@@ -122,9 +126,10 @@ def test_bcsd_precipitation(golden, name, kw):
     fit_groups, _, qm_groups = oracle.wrapper._bcsd_groups(spec['time_grouper'], idx_f, idx_p)
     for c in range(g['Xp'].shape[1]):
         how = 'frame' if spec['time_grouper'] == 'daily_nasa-nex' else 'groupby'
-        st = oracle.bcsd_precipitation_fit(g['ytr'][:, c], fit_groups, kw.get('return_anoms', True), how)
+        st = oracle.bcsd_precipitation_fit(g['ytr'][:, c], fit_groups, kw.get('return_anoms', True), how,
+                                           detrend=kw.get('detrend', False))
         o = oracle.bcsd_precipitation_predict(st, g['Xp'][:, c], qm_groups, kw.get('return_anoms', True))
-        _close(o, g['out64'][:, c], rtol=1e-13, atol=1e-13)
+        _close(o, g['out64'][:, c], rtol=1e-12, atol=1e-12)
 
 
 def test_bcsd_precipitation_bad_climatology():
@@ -228,3 +233,14 @@ def test_edcdf_known_answer(golden):
     assert (oracle.edcdf_predict(st, x + 2, 'difference') == (x + 3) + 2).all()
     assert (oracle.edcdf_predict(st, x * 2, 'ratio') == (x + 3) * 2).all()
     assert (g['difference'] == (x + 3) + 2).all() and (g['ratio'] == (x + 3) * 2).all()
+
+
+@pytest.mark.parametrize('name', ['qm_detrend_equal', 'qm_detrend_longer', 'qm_detrend_f64'])
+def test_qm_detrend(golden, name):
+    """QuantileMapper(detrend=True) (quantile.py:94-98, 127-145; trend.py:40-83) against the live reference."""
+    g = golden(name)
+    for c in range(g['Xp'].shape[1]):
+        st = oracle.quantile_mapper_fit_detrend(g['ytr'][:, c])
+        _close(oracle.quantile_mapper_transform_detrend(g['Xp'][:, c], st), g['out'][:, c], rtol=1e-12, atol=1e-12)
+    out = oracle.pointwise_fit_predict({'name': 'QuantileMapper', 'detrend': True}, None, g['ytr'], g['Xp'])
+    _close(out, g['out'].astype(g['Xp'].dtype), rtol=1e-6, atol=1e-6)

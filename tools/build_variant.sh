@@ -8,5 +8,5 @@ mkdir -p variants
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -fmad=false \
      --expt-relaxed-constexpr -Xptxas -v "$@" -c qm_np1024.cu -o variants/qm_np1024_$name.o 2> variants/$name.ptxas.log
 nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/libsdb_$name.so \
-     sdb_api.o qm_api.o qm_np256.o variants/qm_np1024_$name.o qm_np4096.o qm_np16384.o analog_kernels.o qmr_kernels.o
+     sdb_api.o qm_api.o qm_np256.o variants/qm_np1024_$name.o qm_np4096.o qm_np16384.o analog_kernels.o qmr_kernels.o trend_kernels.o
 echo variants/libsdb_$name.so
