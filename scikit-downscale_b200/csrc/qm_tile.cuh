@@ -25,6 +25,40 @@ constexpr int TILE_CT = SDB_TILE_CT;   // cells per CTA (= warps per CTA): 8 cel
 constexpr int TILE_THREADS = 32 * TILE_CT;
 constexpr int TILE_LMAX = 16;       // longest same-bucket run fixed up locally
 
+// Cache policy of the tile's row accesses and CTA pairing (measured with ncu, profiles/README.md).
+// A CTA touches ONE 32-byte sector per row while DRAM moves 64-byte atoms, so what matters is whether
+// the neighbouring CTA's half meets it in L2:
+//   fit loads      default policy (ld.global.nc): with streaming loads (ld.cs, evict-first) the other half
+//                  was gone before the neighbour asked for it — 11.0 GB read for 5.7 GB of input; now 5.7 GB
+//   predict loads  streaming: keeps the output lines (st.cs) in L2 long enough to be completed — with
+//                  default-policy loads the kernel wrote 9.6 GB for 5.7 GB of output, with ld.cs 7.4 GB
+//   stores         streaming (st.cs): default-policy / st.cg / st.wt stores wrote 11-12 GB
+//   SDB_TILE_CLUSTER n: the tile kernels launch as clusters of n CTAs along x — the CTAs of a cluster own
+//                  ADJACENT 8-cell row segments (the two halves of a 64-byte atom) and start together
+#ifndef SDB_FIT_LD_POLICY
+#define SDB_FIT_LD_POLICY 1      // 0 = ld.cs, 1 = default
+#endif
+#ifndef SDB_PRED_LD_POLICY
+#define SDB_PRED_LD_POLICY 0
+#endif
+#ifndef SDB_ST_POLICY
+#define SDB_ST_POLICY 0          // 0 = st.cs, 1 = default, 2 = st.cg, 3 = st.wt
+#endif
+#ifndef SDB_TILE_CLUSTER
+#define SDB_TILE_CLUSTER 2
+#endif
+template <int POLICY, class P>
+__device__ __forceinline__ auto ld_row(const P* p) { if constexpr (POLICY == 0) return __ldcs(p); else return __ldg(p); }
+#define SDB_LD_ROW(p) ld_row<LDP>(p)
+#if SDB_ST_POLICY == 0
+#define SDB_ST_ROW(p, v) __stcs(p, v)
+#elif SDB_ST_POLICY == 2
+#define SDB_ST_ROW(p, v) __stcg(p, v)
+#elif SDB_ST_POLICY == 3
+#define SDB_ST_ROW(p, v) __stwt(p, v)
+#else
+#define SDB_ST_ROW(p, v) (*(p) = (v))
+#endif
 #ifndef SDB_FIT_BATCH
 #define SDB_FIT_BATCH 8
 #endif
@@ -62,7 +96,7 @@ constexpr size_t predict_tile_smem() { return (size_t)TILE_CT * 2 * TileGeom<E>:
 // 32-byte row segment — and four conflict-free shared stores; it needs 16-byte aligned rows
 // (ld % 4 == 0, aligned base) and a full tile.  Otherwise one 4-byte load per (row, cell).
 // The row numbers are also left in shared memory (rowtab) for the store pass.
-template <int E, int BATCH>
+template <int E, int BATCH, int LDP>
 __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
                                           int64_t c0, const int32_t* __restrict__ rg, int n,
                                           const uint8_t* __restrict__ valid, bool allow_vec,
@@ -104,7 +138,7 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
             for (int j = j0; j < n; j += TILE_THREADS / 2) {
                 const int32_t row = __ldg(rg + j);
                 if (rowtab && quad == 0) rowtab[j] = row;
-                const float4 x = __ldcs(reinterpret_cast<const float4*>(col + (uint64_t)(uint32_t)row * (uint32_t)ld));
+                const float4 x = SDB_LD_ROW(reinterpret_cast<const float4*>(col + (uint64_t)(uint32_t)row * (uint32_t)ld));
                 const int at = skew(j);
                 d0[at] = ok0 ? x.x : 0.0f;
                 d0[NPS + at] = ok1 ? x.y : 0.0f;
@@ -126,7 +160,7 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
                 for (int u = 0; u < B; ++u) {
                     const int j = j0 + (ib + u) * (TILE_THREADS / 2);
                     x[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (j < n) x[u] = __ldcs(reinterpret_cast<const float4*>(col + (uint64_t)(uint32_t)row[u] * (uint32_t)ld));
+                    if (j < n) x[u] = SDB_LD_ROW(reinterpret_cast<const float4*>(col + (uint64_t)(uint32_t)row[u] * (uint32_t)ld));
                 }
 #pragma unroll
                 for (int u = 0; u < B; ++u) {
@@ -156,7 +190,7 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
             for (int u = 0; u < 8; ++u) row[u] = (jb + u * RS < n) ? __ldg(rg + jb + u * RS) : 0;
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                x[u] = (ok && jb + u * RS < n) ? __ldcs(col + (uint64_t)(uint32_t)row[u] * (uint32_t)ld) : 0.0f;
+                x[u] = (ok && jb + u * RS < n) ? SDB_LD_ROW(col + (uint64_t)(uint32_t)row[u] * (uint32_t)ld) : 0.0f;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int j = jb + u * RS;
@@ -183,7 +217,7 @@ qm_fit_tile_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
     const int64_t c0 = (int64_t)blockIdx.x * TILE_CT;
     const int n = len[g];
     const int32_t* rg = rows + (int64_t)g * max_len;
-    load_tile<E, SDB_FIT_BATCH>(tile_f, y, ld, C, c0, rg, n, valid, !no_vec);
+    load_tile<E, SDB_FIT_BATCH, SDB_FIT_LD_POLICY>(tile_f, y, ld, C, c0, rg, n, valid, !no_vec);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = c0 + warp;
@@ -594,7 +628,7 @@ __device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictP
                 const int at = skew(j);
                 float4 v4;
                 v4.x = s0[at]; v4.y = s0[NPS + at]; v4.z = s0[2 * NPS + at]; v4.w = s0[3 * NPS + at];
-                __stcs(reinterpret_cast<float4*>(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out), v4);
+                SDB_ST_ROW(reinterpret_cast<float4*>(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out), v4);
             }
         }
 #else
@@ -603,7 +637,7 @@ __device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictP
             const int at = skew(j);
             float4 v4;
             v4.x = s0[at]; v4.y = s0[NPS + at]; v4.z = s0[2 * NPS + at]; v4.w = s0[3 * NPS + at];
-            __stcs(reinterpret_cast<float4*>(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out), v4);
+            SDB_ST_ROW(reinterpret_cast<float4*>(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out), v4);
         }
 #endif
     } else {
@@ -614,7 +648,7 @@ __device__ __forceinline__ void store_tile(const uint32_t* tileR, const PredictP
             const float* srcp = reinterpret_cast<const float*>(tileR) + cc * NPS;
 #pragma unroll 8
             for (int j = threadIdx.x / TILE_CT; j < n; j += TILE_THREADS / TILE_CT)
-                __stcs(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out, srcp[skew(j)]);
+                SDB_ST_ROW(outp + (uint64_t)(uint32_t)rowtab[j] * (uint32_t)p.ld_out, srcp[skew(j)]);
         }
     }
 }
@@ -653,7 +687,7 @@ qm_predict_tile_kernel(const PredictParams p) {   // SDB_PRED_CTAS: experiment b
         // the fitted sorted values are wanted right after the sort: pull the record into L2 now
         if (lane * 32 < m) asm volatile("prefetch.global.L2 [%0];" :: "l"(S + lane * 32));
     }
-    load_tile<E, SDB_PRED_BATCH>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid, !p.no_vec, rowtab);
+    load_tile<E, SDB_PRED_BATCH, SDB_PRED_LD_POLICY>(tileX, (const float*)p.X, p.ld, p.C, c0, rg, n, p.valid, !p.no_vec, rowtab);
     __syncthreads();
     uint32_t* R = tileR + warp * NPS;
     if (in_range && !active) {
@@ -672,8 +706,20 @@ static int launch_fit_tile(const FitParams& f, cudaStream_t st) {
     const size_t smem = fit_tile_smem<E>();
     if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((f.C + TILE_CT - 1) / TILE_CT), (unsigned)f.n_groups);
+#if SDB_TILE_CLUSTER > 1
+    grid.x = (grid.x + SDB_TILE_CLUSTER - 1) / SDB_TILE_CLUSTER * SDB_TILE_CLUSTER;    // surplus CTAs exit (c >= C)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TILE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SDB_TILE_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SDB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, (const float*)f.y, f.ld, f.C, f.rows, f.len, f.off, f.max_len,
+                                   (float*)f.state, f.state_ld, f.valid, f.nonfinite, f.no_vec));
+#else
     kern<<<grid, TILE_THREADS, smem, st>>>((const float*)f.y, f.ld, f.C, f.rows, f.len, f.off, f.max_len,
                                            (float*)f.state, f.state_ld, f.valid, f.nonfinite, f.no_vec);
+#endif
     SDB_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -687,7 +733,18 @@ static int launch_predict_tile(const PredictParams& p, cudaStream_t st) {
     const size_t smem = predict_tile_smem<E>() + SDB_PRED_EXTRA_SMEM;
     if (smem > 48 * 1024) SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((p.C + TILE_CT - 1) / TILE_CT), (unsigned)p.n_groups);
+#if SDB_TILE_CLUSTER > 1
+    grid.x = (grid.x + SDB_TILE_CLUSTER - 1) / SDB_TILE_CLUSTER * SDB_TILE_CLUSTER;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(TILE_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = SDB_TILE_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    SDB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
+#else
     kern<<<grid, TILE_THREADS, smem, st>>>(p);
+#endif
     SDB_CUDA_OK(cudaGetLastError());
     return 0;
 }

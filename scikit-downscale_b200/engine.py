@@ -12,6 +12,7 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -165,7 +166,8 @@ def alloc_state(dtype, n_cells: int, device, sort_table: GroupTable, mean_table:
         raise NotImplementedError(f'time groups longer than {lib.sdb_max_group_len()} steps are not supported yet '
                                   f'(got {sort_table.max_len})')
     lens = sort_table.len.astype(np.int64)
-    padded = (lens + 3) // 4 * 4                       # keep every group 16-byte aligned inside a record
+    align = int(os.environ.get('SDB_STATE_ALIGN', '4'))    # elements; experiment knob (sector-aligned groups: 8)
+    padded = (lens + align - 1) // align * align       # keep every group 16-byte aligned inside a record
     off = np.concatenate(([0], np.cumsum(padded)[:-1])).astype(np.int64)
     state_ld = int(padded.sum())
     mt = mean_table if mean_table is not None else sort_table

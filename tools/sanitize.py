@@ -12,8 +12,9 @@ import torch
 import synth
 import skdownscale_b200  # noqa
 from skdownscale_b200 import _lib, engine
-from skdownscale_b200.pointwise_models import (AnalogRegression, BcsdPrecipitation, BcsdTemperature, PureAnalog,
-                                               QuantileMapper)
+from skdownscale_b200.pointwise_models import (AnalogRegression, BcsdPrecipitation, BcsdTemperature,
+                                               EquidistantCdfMatcher, PureAnalog, QuantileMapper,
+                                               QuantileMappingReressor)
 
 dev = torch.device('cuda:0')
 T, C = 1200, 11
@@ -39,5 +40,22 @@ A, ya, Aq = synth.analog(300, 90, 3, 3, 4)
 for m in (PureAnalog(n_analogs=10, kind='weight_analogs'), AnalogRegression(n_analogs=10), AnalogRegression(n_analogs=40)):
     m.fit_batched(engine.as_device(A, dev), engine.as_device(ya, dev))
     m.predict_batched(engine.as_device(Aq, dev), want_idx=True)
+# AnalogRegression(thresh=...): logistic + min-norm epilogue (queries whose analogs are all below the
+# threshold only raise the flag)
+m = AnalogRegression(n_analogs=12, thresh=-0.5)
+m.fit_batched(engine.as_device(A, dev), engine.as_device(ya, dev))
+m.predict_batched(engine.as_device(Aq, dev))
+# CDF-to-CDF regressors, every tail mode; detrending mappers; non-default Cunnane tails
+for ex in (None, 'min', 'max', 'both', '1to1'):
+    for est in (QuantileMappingReressor(extrapolate=ex, n_endpoints=5), EquidistantCdfMatcher(kind='ratio', extrapolate=ex, n_endpoints=5)):
+        est.fit_batched(engine.as_device(Xtr[:400], dev), engine.as_device(ytr[:400], dev))
+        est.predict_batched(engine.as_device(Xp[:700], dev))
+for model, a, b, c in ((BcsdTemperature(qm_kwargs={'detrend': True}), Xtr, ytr, Xp),
+                       (BcsdPrecipitation(qm_kwargs={'detrend': True, 'qt_kwargs': {'extrapolate': 'max', 'n_endpoints': 4}}), Ptr, pytr, Pp)):
+    model.fit_batched(engine.as_device(a, dev), engine.as_device(b, dev), idx)
+    model.predict_batched(engine.as_device(c, dev), idx)
+q = QuantileMapper(detrend=True, qt_kwargs={'extrapolate': None})
+q.fit_batched(engine.as_device(ytr[:300], dev))
+q.transform_batched(engine.as_device(Xp[:500], dev))
 torch.cuda.synchronize()
 print('sanitize workload done')
