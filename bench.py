@@ -204,6 +204,18 @@ def ncu_traffic(kernel: str, units: float):
         return None
 
 
+def ncu_limiter(kernel: str):
+    """What actually bounds ``kernel`` according to the committed ncu capture: pipe / issue utilisation
+    (the path is a sorting network — the ALU pipe that executes VIMNMX and dependency latency, not HBM)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+            k = json.load(f)['kernels'][kernel]
+        return {m: k[m] for m in ('alu_pipe_pct', 'fma_pipe_pct', 'issue_active_pct', 'dram_throughput_pct', 'registers')
+                if m in k}
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -368,6 +380,8 @@ def run_b200(a):
                          'frac': ach / peak, 'traffic': ncu_traffic('qm_predict_tile_kernel<32,true>', float(C) * T),
                          'traffic_source': 'profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)',
                          'peak_source': peak_src,
+                         'limiter_from_ncu': {'qm_predict_tile_kernel<32,true>': ncu_limiter('qm_predict_tile_kernel<32,true>'),
+                                              'qm_fit_tile_kernel<32>': ncu_limiter('qm_fit_tile_kernel<32>')},
                          'algorithmic_bytes_per_cell_timestep': ALG_BYTES_PREDICT, 'kernel_ms': pms,
                          'whole_step': {'achieved': ach_step, 'frac': ach_step / peak,
                                         'algorithmic_bytes_per_cell_timestep': ALG_BYTES_STEP}},
