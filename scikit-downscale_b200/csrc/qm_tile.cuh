@@ -441,12 +441,16 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
                 sum -= (double)xh[e];
             }
         } else {
+            // Bucket 0 is reserved for the values AT the lower bound, everything above it starts at bucket 1
+            // (still monotone).  Zero-inflated precipitation: the run of exact zeros then never shares a
+            // bucket with a tiny positive value — that mix is not sorted by value inside the bucket and
+            // would send the whole group to the exact 64-bit sort (a 20x straggler that holds its CTA).
             const float range = hi32 - lo32;
-            const float scale = (range > 0.0f && isfinite(range)) ? (float)QTOP / range : 0.0f;
+            const float scale = (range > 0.0f && isfinite(range)) ? (float)(QTOP - 1u) / range : 0.0f;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const float t = (xh[e] - lo32) * scale;
-                uint32_t q = __float2uint_rd(t);            // saturating: negative and NaN map to 0
+                uint32_t q = __float2uint_rd(t) + ((xh[e] > lo32) ? 1u : 0u);   // saturating: negative and NaN map to 0
                 q = q > QTOP ? QTOP : q;
                 const uint32_t w = (q << LOG) + (uint32_t)(j0 + e);
                 v[e].k = (e < nj) ? w : pad0 + (uint32_t)e * G::PAD_STEP;
@@ -504,19 +508,10 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
         tie_carry = __shfl_sync(0xffffffffu, first_end, higher ? (__ffs(higher) - 1) : lane);
     }
 
-    // isolated pairs only (no two tie bits adjacent, also across lanes): the register path below can
-    // patch them in place; longer tie runs (e.g. the zeros of precipitation) take the staged loop
-    bool pairs_only = false;
-    if (mode == 2) {
-        const uint32_t nxt_tie0 = __shfl_down_sync(0xffffffffu, bm_tie & 1u, 1);
-        const bool adjacent = ((bm_tie & (bm_tie >> 1)) != 0) || ((lane < 31) && ((bm_tie >> (E - 1)) & 1u) && nxt_tie0);
-        pairs_only = !__any_sync(0xffffffffu, adjacent);
-    }
-    if ((mode == 0 || pairs_only) && same && !p.rank_out && (E % 4 == 0) && quad_ok) {
+    if ((mode == 0 || mode == 2) && same && !p.rank_out && (E % 4 == 0) && quad_ok) {
         // the common case: same length and (almost) one member per bucket — the member at sorted
         // position pos takes the fitted order statistic S[pos]; the lane's 32 values are 8 vector loads
         float sv[E + 1];
-#pragma unroll
         // quads past the group's last one re-read that last quad (positions >= n only feed padding slots);
         // the last quad may reach up to 3 values into the 16-byte alignment gap behind the group, which
         // belongs to the cell's record
@@ -531,16 +526,20 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
 #pragma unroll
             for (int e = 0; e < E; ++e) finish((int)(v[e].k & IDX), sv[e]);    // padding positions land in slots >= n of R
         } else {
-            // same scatter with the isolated same-bucket pairs patched: an inverted pair exchanges its
-            // members, an exactly tied pair both take the higher order statistic (tie-max rank)
-            sv[E] = (j0 + E < n) ? __ldg(S + j0 + E) : 0.0f;
+            // same scatter with the same-bucket structure patched in registers: an isolated inverted pair
+            // exchanges its members; every position of an exact-tie run (any length — the zeros of
+            // precipitation are one run of hundreds) takes the order statistic at the END of its run
+            // (tie-max rank): a backward scan over the lane's positions, seeded with the value at the run
+            // end in a later lane when the lane's last position is still inside a run
+            float run_val = ((bm_tie >> (E - 1)) & 1u) ? __ldg(S + tie_carry - 1) : 0.0f;
             const uint32_t prv_last_k = __shfl_up_sync(0xffffffffu, v[E - 1].k, 1);
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
+            for (int e = E - 1; e >= 0; --e) {
                 uint32_t w = v[e].k;
                 if ((bm_gt >> e) & 1u) w = (e == E - 1) ? nxt_first : v[e == E - 1 ? e : e + 1].k;
                 else if ((e == 0) ? prev_gt : ((bm_gt >> (e == 0 ? 0 : e - 1)) & 1u)) w = (e == 0) ? prv_last_k : v[e == 0 ? e : e - 1].k;
-                finish((int)(w & IDX), ((bm_tie >> e) & 1u) ? sv[e + 1] : sv[e]);
+                run_val = ((bm_tie >> e) & 1u) ? run_val : sv[e];
+                finish((int)(w & IDX), run_val);
             }
         }
     } else if (mode == 3) {

@@ -18,12 +18,13 @@ import torch  # noqa: E402
 import synth  # noqa: E402
 import skdownscale_b200  # noqa: F401,E402
 from skdownscale_b200.pointwise_models import (AnalogRegression, BcsdPrecipitation, BcsdTemperature,  # noqa: E402
-                                               PureAnalog, QuantileMapper)
+                                               EquidistantCdfMatcher, PureAnalog, QuantileMapper,
+                                               QuantileMappingReressor)
 
 dev = torch.device('cuda:0')
 
 
-def timed(fn, warmup=1, steps=3):
+def timed(fn, warmup=3, steps=8):
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -50,7 +51,8 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(0)
     if not only_analog:
         qm_paths(gen)
-    analog_paths(gen)
+    if '--qm' not in sys.argv:
+        analog_paths(gen)
 
 
 def qm_paths(gen):
@@ -62,6 +64,18 @@ def qm_paths(gen):
     qm = QuantileMapper()
     report('QuantileMapper 10000 cells x 10950 (one 10950-step group per cell)', C, T,
            timed(lambda: (qm.fit_batched(y), qm.transform_batched(x))), 12)
+    # the "next" estimators on the same block
+    qd = QuantileMapper(detrend=True)
+    report('QuantileMapper(detrend=True) 10000 cells x 10950', C, T,
+           timed(lambda: (qd.fit_batched(y), qd.transform_batched(x))), 12)
+    qr = QuantileMappingReressor(extrapolate='1to1')
+    report('QuantileMappingReressor(1to1) fit+predict 10000 cells x 10950', C, T,
+           timed(lambda: (qr.fit_batched(x, y), qr.predict_batched(x))), 16)
+    qr.fit_batched(x, y)
+    report('QuantileMappingReressor(1to1) predict only', C, T, timed(lambda: qr.predict_batched(x)), 8)
+    ed = EquidistantCdfMatcher(kind='difference')
+    report('EquidistantCdfMatcher(difference) fit+predict 10000 cells x 10950', C, T,
+           timed(lambda: (ed.fit_batched(x, y), ed.predict_batched(x))), 16)
     del y, x
 
     # config 3 (per-GPU shard): BcsdPrecipitation, zero-inflated
@@ -103,6 +117,7 @@ def analog_paths(gen):
     # config 4/5 style: analog models, k = 10, 3 predictors
     for name, model, T, Tq, C in (('PureAnalog(k=10, mean_analogs) 1024 cells x 18250', PureAnalog(n_analogs=10, kind='mean_analogs'), 18250, 18250, 1024),
                                   ('AnalogRegression(k=10) 1024 cells x 10950', AnalogRegression(n_analogs=10), 10950, 10950, 1024),
+                                  ('AnalogRegression(k=10, thresh=0) 1024 cells x 10950', AnalogRegression(n_analogs=10, thresh=0.0), 10950, 10950, 1024),
                                   ('AnalogRegression(k=200) 128 cells x 10950', AnalogRegression(n_analogs=200), 10950, 10950, 128)):
         X = torch.randn((T, 3, C), device=dev, generator=gen)
         w = torch.tensor([1.0, 0.5, -0.3], device=dev)[None, :, None]
