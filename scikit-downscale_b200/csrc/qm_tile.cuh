@@ -345,6 +345,89 @@ static __device__ __noinline__ float mapped_value_general(const PredictParams& p
     return (float)inverse_cdf_acc(rk, n, m, Sat, pp_denominator(n, cu), pp_denominator(m, cu), cu);
 }
 
+// The same map for the interior of the fitted CDF with the per-(cell, group) constants hoisted: the
+// plotting positions (i - alpha) / den are formed with one reciprocal per group and an exact-residual FMA
+// correction (RN(1/den) → q0 = a * rc → r = fma(-q0, den, a) → fma(r, rc, q0): the correctly rounded
+// quotient), which leaves ONE true division per value (the slope) where the generic routine spends eight.
+// Tails (a handful of ranks when T_pred > T_fit) and degenerate groups go to the generic routine.
+struct GroupMap {
+    double dn, dm, rdn, rdm, p1, pm, alpha;
+    double a_lo, b_lo, a_hi, b_hi;      // value = a * q + b beyond the fitted positions (valid when `tails`)
+    int n, m;
+    bool tails;
+};
+__device__ __forceinline__ double fdiv(double a, double den, double rc) {
+    const double q0 = a * rc;
+    return fma(fma(-q0, den, a), rc, q0);
+}
+__device__ __forceinline__ GroupMap make_group_map(const PredictParams& p, int n, int m) {
+    const Cunnane cu = cunnane_of(p);
+    GroupMap g;
+    g.n = n; g.m = m; g.alpha = cu.alpha;
+    g.dn = pp_denominator(n, cu); g.dm = pp_denominator(m, cu);
+    g.rdn = 1.0 / g.dn; g.rdm = 1.0 / g.dm;
+    g.p1 = pp_of(1, g.dm, cu); g.pm = pp_of(m, g.dm, cu);
+    g.tails = false;
+    g.a_lo = g.b_lo = g.a_hi = g.b_hi = 0.0;
+    return g;
+}
+// The two tail lines of a (cell, group), once per warp: lane 0 fits the lower one, lane 31 the upper
+// one in the same instruction stream (the per-value generic routine refits the 10-point line for every
+// rank that falls outside — four ranks per group when T_pred = 3 T_fit, each on a different lane: they
+// made up a third of the instructions of the interpolation path).  A tail that does not extrapolate
+// clamps to the end value (a = 0).
+__device__ __forceinline__ void fit_group_tails(const PredictParams& p, GroupMap& g, const float* __restrict__ S, int lane) {
+    const Cunnane cu = cunnane_of(p);
+    double a = 0.0, b = 0.0;
+    if (lane == 0 || lane == 31) {
+        const bool low = (lane == 0);
+        auto Sat = [&](int i) -> double { return (double)__ldg(S + i); };
+        const int ne = g.m < cu.ne ? g.m : cu.ne;
+        if (low ? cu.lo : cu.hi) ols_tail(Sat, low ? 1 : g.m - ne + 1, ne, g.dm, cu, a, b);
+        else b = Sat(low ? 0 : g.m - 1);
+    }
+    g.a_lo = __shfl_sync(0xffffffffu, a, 0);  g.b_lo = __shfl_sync(0xffffffffu, b, 0);
+    g.a_hi = __shfl_sync(0xffffffffu, a, 31); g.b_hi = __shfl_sync(0xffffffffu, b, 31);
+    g.tails = true;
+}
+// position of quantile q inside the fitted CDF (pure arithmetic, no loads): j = 0 → take the generic routine
+struct InterpLoc { int j; double q, xj, xj1; };
+__device__ __forceinline__ InterpLoc interp_locate(const GroupMap& g, int rk) {
+    InterpLoc L;
+    L.j = 0;
+    L.q = fdiv((double)rk - g.alpha, g.dn, g.rdn);
+    L.xj = L.xj1 = 0.0;
+    if (g.m < 2) return L;
+    if (g.tails && L.q < g.p1) { L.j = -1; return L; }    // value = a_lo * q + b_lo
+    if (g.tails && L.q > g.pm) { L.j = -2; return L; }
+    if (!(L.q >= g.p1) || !(L.q < g.pm)) return L;
+    int j = (int)floor(L.q * g.dm + g.alpha);
+    j = j < 1 ? 1 : (j > g.m - 1 ? g.m - 1 : j);
+    double xj = fdiv((double)j - g.alpha, g.dm, g.rdm), xj1 = fdiv((double)(j + 1) - g.alpha, g.dm, g.rdm);
+    if (xj > L.q) {                                      // the guess is off by at most one
+        if (j == 1) return L;
+        --j; xj1 = xj; xj = fdiv((double)j - g.alpha, g.dm, g.rdm);
+    } else if (xj1 <= L.q) {
+        if (j + 1 > g.m - 1) return L;
+        ++j; xj = xj1; xj1 = fdiv((double)(j + 1) - g.alpha, g.dm, g.rdm);
+    }
+    if (xj > L.q || xj1 <= L.q) return L;               // never expected: the generic routine stays exact
+    L.j = j; L.xj = xj; L.xj1 = xj1;
+    return L;
+}
+__device__ __forceinline__ float interp_value(const InterpLoc& L, float y0, float y1) {
+    if (L.q == L.xj) return y0;
+    const double slope = ((double)y1 - (double)y0) / (L.xj1 - L.xj);
+    return (float)(slope * (L.q - L.xj) + (double)y0);
+}
+// one value, self-contained and out of line (the rare exact-sort path)
+static __device__ __noinline__ float mapped_value_interp(const PredictParams& p, const float* __restrict__ S, int rk, int n, int m) {
+    const GroupMap g = make_group_map(p, n, m);
+    const InterpLoc L = interp_locate(g, rk);
+    if (L.j == 0) return mapped_value_general(p, S, rk, n, m);
+    return interp_value(L, __ldg(S + L.j - 1), __ldg(S + L.j));
+}
+
 // ---------------------------------------------------------------- predict
 // One warp maps one (cell, group): the group's inputs are in the shared row myX, the outputs
 // (float bits) are left in the shared row R.  See the header comment of this file and DESIGN.md §4.
@@ -549,7 +632,7 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
         for (int j = j0; j < j1; ++j) {
             const int rk = (int)Xu[skew(j)];
             if (p.rank_out) p.rank_out[(int64_t)rg[j] * p.ld_out + c] = rk;
-            finish(j, same ? __ldg(S + rk - 1) : mapped_value_general(p, S, rk, n, m));
+            finish(j, same ? __ldg(S + rk - 1) : mapped_value_interp(p, S, rk, n, m));
         }
     } else {
         // every other case (ties / swapped pairs / T_pred != T_fit / rank instrumentation): the exact
@@ -573,7 +656,14 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
             Xu[rb + e] = (Xu[rb + e] & IDX) | ((uint32_t)rk << LOG);
         }
         __syncwarp();
-        // pass B: four positions at a time — the fitted values are fetched together, then finished
+        // pass B: four positions at a time — the fitted values are fetched together, then finished.
+        // T_pred != T_fit: the four CDF positions are located first (arithmetic only), then their eight
+        // fitted values are requested together, then interpolated — the loads of a batch overlap
+        GroupMap gmap;
+        if (!same) {
+            gmap = make_group_map(p, n, m);
+            if (n > m) fit_group_tails(p, gmap, S, lane);       // ranks outside the fitted positions exist only then
+        }
         for (int e0 = 0; e0 < E; e0 += 4) {
             if (j0 + e0 >= n) break;
             uint32_t member[4];
@@ -593,12 +683,33 @@ __device__ __forceinline__ void map_cell_group(const PredictParams& p, float* my
                 }
                 val[d] = (same && pos < n) ? __ldg(S + rk[d] - 1) : 0.0f;
             }
+            if (!same) {
+                InterpLoc loc[4];
+                float y0[4], y1[4];
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    loc[d] = interp_locate(gmap, (j0 + e0 + d < n) ? rk[d] : 1);
+                    if (j0 + e0 + d >= n) loc[d].j = 0;
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    y0[d] = loc[d].j > 0 ? __ldg(S + loc[d].j - 1) : 0.0f;
+                    y1[d] = loc[d].j > 0 ? __ldg(S + loc[d].j) : 0.0f;
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d)
+                    if (j0 + e0 + d < n)
+                        val[d] = loc[d].j > 0 ? interp_value(loc[d], y0[d], y1[d])
+                               : loc[d].j == -1 ? (float)(gmap.a_lo * loc[d].q + gmap.b_lo)
+                               : loc[d].j == -2 ? (float)(gmap.a_hi * loc[d].q + gmap.b_hi)
+                               : mapped_value_general(p, S, rk[d], n, m);
+            }
 #pragma unroll
             for (int d = 0; d < 4; ++d) {
                 const int pos = j0 + e0 + d;
                 if (pos < n) {
                     if (p.rank_out) p.rank_out[(int64_t)rg[member[d]] * p.ld_out + c] = rk[d];
-                    finish((int)member[d], same ? val[d] : mapped_value_general(p, S, rk[d], n, m));
+                    finish((int)member[d], val[d]);
                 }
             }
         }

@@ -352,7 +352,7 @@ def _bcsd_temperature_vs_oracle_ranks(dev, anoms):
 
 
 @pytest.mark.parametrize('family', ['tile', 'scalar'])
-@pytest.mark.parametrize('case', ['outlier', 'clusters', 'constant', 'two_values'])
+@pytest.mark.parametrize('case', ['outlier', 'clusters', 'constant', 'two_values', 'zeros_and_tiny', 'ties_and_pairs'])
 @pytest.mark.parametrize('model', ['T', 'P'])
 def test_tile_kernel_bucket_fixups(dev, case, model, family):
     with force_generic(family):
@@ -381,6 +381,19 @@ def _tile_kernel_bucket_fixups(dev, case, model):
         Xp[:] = np.float32(7.25)
     elif case == 'two_values':
         Xp[:] = np.where(rng.random((T, C)) < 0.6, np.float32(0.0), np.float32(1e-7))
+    elif case == 'zeros_and_tiny':
+        # zero-inflated series whose smallest positive values would share the zeros' bucket under a
+        # plain linear quantisation (range ~60 → bucket width 1.4e-5)
+        wet = rng.random((T, C)) > 0.55
+        Xp[:] = np.where(wet, rng.gamma(0.8, 6.0, (T, C)), 0.0).astype(np.float32)
+        Xp[3::97, :] = np.float32(3e-6)
+        Xp[5::101, 2] = np.float32(7e-6)
+    elif case == 'ties_and_pairs':
+        # long exact-tie runs (values on a 0.5 grid) next to isolated near-duplicates one ulp apart
+        Xp[:] = (np.round(Xp * 2) / 2).astype(np.float32)
+        near = (np.float32(11.25).view(np.int32) + np.arange(1, 6, dtype=np.int32)).view(np.float32)
+        for k, v in enumerate(near):
+            Xp[40 + 31 * k::360, 1::2] = v
     groups = oracle.groups_from_keys(oracle.month_keys(idx))
     if model == 'T':
         m = pm().BcsdTemperature(return_anoms=False)
@@ -400,6 +413,10 @@ def _tile_kernel_bucket_fixups(dev, case, model):
         assert np.array_equal(rank[:, c], r), f'{case}/{model}: rank mismatch in cell {c}'
         if case != 'outlier':
             assert_close(out[:, c], o.astype(np.float32), scale=np.std(ytr[:, c]))
+    # the same call without rank instrumentation takes the register paths (one member per bucket, tie
+    # runs / isolated pairs patched in registers, exact-sort fallback): identical field
+    out2 = m.predict_batched(eng().as_device(Xp, dev), idx).cpu().numpy()
+    assert np.array_equal(out2, out, equal_nan=True), f'{case}/{model}: register path differs from the staged path'
 
 
 @pytest.mark.parametrize('generic', ['tile', 'generic', 'scalar'])
