@@ -486,6 +486,49 @@ def test_bcsd_abs_multiset_property(dev):
         torch.testing.assert_close(out[sel], _expected_rank_map(Xtr[sel], ytr[sel]), rtol=0, atol=0)
 
 
+def test_full_shard_headline_and_precipitation(dev):
+    """BASELINE.json's full per-GPU shard (129 600 cells x 10 950 days, the 8-GPU slice of the 720x1440
+    grid): (a) BcsdTemperature fit+predict — cells sampled at the ends of the shard, around tile
+    boundaries and at random are compared with the oracle (1e-5), which exercises the full-size launch
+    geometry and 64-bit addressing; (b) the per-month quantile map of X onto y's distribution
+    (BcsdPrecipitation, return_anoms=False) — for two whole months EVERY cell must equal the fitted
+    order statistic at its tie-max rank (exact, computed independently with torch)."""
+    if torch.cuda.get_device_properties(dev).total_memory < 60e9:
+        pytest.skip('needs ~35 GB of device memory')
+    T, C = 10950, 129600
+    idx = synth.daily_index(T)
+    gen = torch.Generator(device=dev).manual_seed(2024)
+    s = torch.sin(2 * torch.pi * torch.arange(T, device=dev, dtype=torch.float32) / 365.25)[:, None]
+
+    def field(mean, amp, sd):
+        x = torch.randn((T, C), device=dev, dtype=torch.float32, generator=gen)
+        return x.mul_(sd).add_(mean + amp * s)
+
+    Xtr, ytr, Xp = field(15.0, 10.0, 3.0), field(14.0, 12.0, 2.0), field(16.5, 10.0, 3.0)
+    m = pm().BcsdTemperature(return_anoms=True)
+    m.fit_batched(Xtr, ytr, idx)
+    out = m.predict_batched(Xp, idx)
+    m._state.check_finite()
+    rng = np.random.default_rng(5)
+    cells = sorted({0, 1, 7, 8, 9, C // 2, C - 9, C - 8, C - 1, *rng.integers(0, C, 12).tolist()})
+    groups = oracle.groups_from_keys(oracle.month_keys(idx))
+    got = out[:, cells].cpu().numpy()
+    xs, ys, ps = (a[:, cells].cpu().numpy() for a in (Xtr, ytr, Xp))
+    for k in range(len(cells)):
+        st = oracle.bcsd_temperature_fit(xs[:, k], ys[:, k], groups)
+        o = oracle.bcsd_temperature_predict(st, ps[:, k], groups, groups, True)
+        assert_close(got[:, k], o.astype(np.float32), scale=np.std(ys[:, k]))
+    del out, m
+    torch.cuda.empty_cache()
+    q = pm().BcsdPrecipitation(return_anoms=False)
+    q.fit_batched(Xtr, ytr, idx)
+    out = q.predict_batched(Xp, idx)
+    month = torch.as_tensor(np.asarray(idx.month), device=dev)
+    for mo in (2, 8):
+        sel = month == mo
+        torch.testing.assert_close(out[sel], _expected_rank_map(Xp[sel], ytr[sel]), rtol=0, atol=0)
+
+
 # ------------------------------------------------------------------ GARD
 @pytest.mark.parametrize('kind', ['best_analog', 'mean_analogs', 'weight_analogs', 'sample_analogs'])
 @pytest.mark.parametrize('suffix,thresh', [('', None), ('_thresh', 0.0)])

@@ -113,3 +113,32 @@ def test_estimator_surface_and_no_cpu_fallback():
         BcsdTemperature(time_grouper='daily_nasa-nex', qm_kwargs={'detrend': True})._pre_fit()
     with pytest.raises(TypeError):
         QuantileMapper(qt_kwargs={'gamma': 1}).fit_batched(None)       # CunnaneTransformer has no such argument
+
+
+def test_next_row_estimators_host_side():
+    """Constructor / option validation of the "next" estimators runs on the host (no GPU needed) and follows
+    the reference: quantile.py:183-191, 577-592 (n_endpoints, kind), 420-432 (Cunnane keywords), trend.py:31-32."""
+    from skdownscale_b200 import _lib
+    from skdownscale_b200.pointwise_models import EquidistantCdfMatcher, QuantileMappingReressor
+    from skdownscale_b200.pointwise_models.quantile import check_lt_kwargs, cunnane_opts
+    from sklearn.base import clone
+    with pytest.raises(ValueError, match='n_endpoints'):
+        QuantileMappingReressor(n_endpoints=1)
+    with pytest.raises(NotImplementedError):
+        EquidistantCdfMatcher(kind='product')
+    m = EquidistantCdfMatcher(kind='ratio', extrapolate='1to1', n_endpoints=4)
+    assert clone(m).get_params() == {'kind': 'ratio', 'extrapolate': '1to1', 'n_endpoints': 4, 'max_ratio': None}
+    assert m._kind == _lib.QMR_EDCDF_RATIO and QuantileMappingReressor()._kind == _lib.QMR_REGRESSOR
+    assert cunnane_opts(None) is None and cunnane_opts({'alpha': 0.4, 'extrapolate': 'both'}) is None
+    o = cunnane_opts({'extrapolate': 'min', 'n_endpoints': 3, 'alpha': 0.1})
+    # the reference never hands alpha / beta to plotting_positions (quantile.py:462): always 0.4
+    assert (o.alpha, o.beta, o.n_endpoints, o.extrapolate) == (0.4, 0.4, 3, 1)
+    assert cunnane_opts({'extrapolate': None}).extrapolate == 0 and cunnane_opts({'extrapolate': '1to1'}).extrapolate == 0
+    with pytest.raises(ValueError):
+        cunnane_opts({'extrapolate': 'upwards'})
+    check_lt_kwargs(None)
+    check_lt_kwargs({'lr_kwargs': {'fit_intercept': True}})
+    with pytest.raises(TypeError):
+        check_lt_kwargs({'degree': 2})
+    with pytest.raises(NotImplementedError):
+        check_lt_kwargs({'lr_kwargs': {'positive': True}})
