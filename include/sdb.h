@@ -269,6 +269,24 @@ int sdb_bcsd_combine(int mode, const double* mapped, const double* shift, int64_
                      const void* y_climo, int climo_dtype, int64_t ld_climo, int return_anoms,
                      void* out, int out_dtype, int64_t ld_out, const uint8_t* cell_valid, void* stream);
 
+/*
+ * PureRegression (gard.py:367-504) — SURVEY.md §8(f) row 4: one least-squares fit per cell on the rows whose
+ * target exceeds thresh (all rows without one), its in-sample RMSE, and — with a threshold — the logistic
+ * exceedance model of all rows (exceedance_prob = P(class 1), gard.py:467; solved to its optimum like
+ * sdb_analog_predict's).  model: device float64 [n_cells, sdb_pure_regression_model_ld()], private layout.
+ * A cell with NO row above thresh makes the reference's LinearRegression raise on an empty selection
+ * (gard.py:435): the kernel ORs 4 into *nonfinite.  float32 inputs: the reference fits in float32 through
+ * LAPACK, here the accumulation is float64 — parity to the stated tolerance, not to the bit.
+ *   X_train [T_fit, p, C], y_train [T_fit, C], X_query [T_q, p, C] (dtype); out [T_q, 3, C] (out_dtype).
+ */
+int sdb_pure_regression_model_ld(void);
+int sdb_pure_regression_fit(const void* X_train, const void* y_train, int dtype, int64_t ld, int64_t n_cells,
+                            int t_fit, int n_features, int has_thresh, double thresh, double logistic_c,
+                            double* model, const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+int sdb_pure_regression_predict(const void* X_query, int dtype, int64_t ld, int64_t n_cells, int t_query,
+                                int n_features, const double* model, void* out, int out_dtype, int64_t ld_out,
+                                const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

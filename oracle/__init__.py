@@ -51,5 +51,6 @@ from .gard import (  # noqa: F401
     analog_regression_predict,
     knn_bruteforce,
     pure_analog_predict,
+    pure_regression_fit_predict,
 )
 from .wrapper import pointwise_fit_predict  # noqa: F401

@@ -172,3 +172,44 @@ def analog_regression_predict(X_train, y_train, X_query, n_analogs: int = 200, t
         pred = Q[i].astype(np.float64) @ coef + intercept           # gard.py:221
         out[i] = (pred, prob, err)                                  # gard.py:224
     return (out, inds) if return_inds else out
+
+
+def pure_regression_fit_predict(X_train, y_train, X_query, thresh=None, logistic_C: float = 1.0):
+    """PureRegression.fit + predict for ONE cell (gard.py:367-504) — SURVEY §8(f) row 4.
+
+    One least-squares fit per cell on the rows whose target exceeds ``thresh`` (all rows without a
+    threshold), in the dtype of the inputs like sklearn's LinearRegression (float32 inputs are fitted
+    in float32 — LAPACK details differ between drivers at the 1e-6 level, so float32 parity is to the
+    tolerance, float64 parity to 1e-9); ``prediction_error`` = the in-sample RMSE, the same for every
+    step; ``exceedance_prob`` = P(class 1) of a logistic regression of ``y > thresh`` on ALL rows
+    (gard.py:417, 467 — note AnalogRegression reports P(class 0)), 1.0 without a threshold or when
+    every row exceeds (gard.py:418-430: the one-class case mutates ``thresh`` to None; with no row
+    above the threshold the linear fit then fails on an empty set and the reference raises).
+    Returns float64 [Tq, 3] in ``output_names`` order."""
+    X = np.asarray(X_train)
+    if X.ndim == 1:
+        X = X[:, None]
+    y = np.asarray(y_train).reshape(-1)
+    Q = np.asarray(X_query)
+    if Q.ndim == 1:
+        Q = Q[:, None]
+    prob = np.ones(len(Q), dtype=np.float64)
+    exceed = np.ones(len(y), dtype=bool)
+    if thresh is not None:
+        exceed = y > thresh
+        if exceed.all() or not exceed.any():
+            if not exceed.any():
+                raise ValueError('Found array with 0 sample(s) (shape=(0, %d)) while a minimum of 1 is required '
+                                 'by LinearRegression.' % X.shape[1])
+        else:
+            w, c0 = logistic_fit_exact(X.astype(np.float64), exceed, logistic_C)
+            z = Q.astype(np.float64) @ w + c0
+            prob = 1.0 / (1.0 + np.exp(-z))                          # predict_proba[:, 1]
+    xs, ys = X[exceed], y[exceed]
+    xo, yo = xs.mean(axis=0), ys.mean()
+    coef, *_ = np.linalg.lstsq(xs - xo, ys - yo, rcond=None)
+    intercept = yo - xo @ coef
+    resid = ys - (xs @ coef + intercept)
+    err = float(np.sqrt(np.mean(resid.astype(np.float64) ** 2)))
+    pred = Q @ coef + intercept
+    return np.stack([pred.astype(np.float64), prob, np.full(len(Q), err)], axis=1)

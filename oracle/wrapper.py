@@ -42,7 +42,7 @@ def pointwise_fit_predict(spec: dict, X_train, y_train, X_pred, index_fit=None, 
     X_pred = np.asarray(X_pred)
     C = X_pred.shape[-1]
     Tp = X_pred.shape[0]
-    multi = name in ('PureAnalog', 'AnalogRegression')
+    multi = name in ('PureAnalog', 'AnalogRegression', 'PureRegression')
     out = np.full((Tp, 3, C) if multi else (Tp, C), np.nan, dtype=X_pred.dtype)   # core.py:129-135
     first = X_train if name != 'QuantileMapper' else y_train
     first = np.asarray(first)
@@ -82,6 +82,9 @@ def pointwise_fit_predict(spec: dict, X_train, y_train, X_pred, index_fit=None, 
             res = gard.analog_regression_predict(np.asarray(X_train)[:, :, c], np.asarray(y_train)[:, c],
                                                  X_pred[:, :, c], spec.get('n_analogs', 200),
                                                  spec.get('thresh'), logistic_C=spec.get('logistic_C', 1.0))
+        elif name == 'PureRegression':
+            res = gard.pure_regression_fit_predict(np.asarray(X_train)[:, :, c], np.asarray(y_train)[:, c],
+                                                   X_pred[:, :, c], spec.get('thresh'), spec.get('logistic_C', 1.0))
         else:
             raise ValueError(name)
         if multi:

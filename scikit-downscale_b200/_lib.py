@@ -71,6 +71,11 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'sdb_bcsd_combine': (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    'sdb_pure_regression_model_ld': (c_int, []),
+    'sdb_pure_regression_fit': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_double,
+                                        c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sdb_pure_regression_predict': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int,
+                                            c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -173,9 +173,8 @@ __device__ void sym_minnorm_solve(const double (&A)[P][P], const double (&b)[P],
 // with lbfgs stopped at tol = 1e-4, so it agrees with this optimum to ~1e-4): returns
 // predict_proba(X)[0, 0] = P(class 0) at the query point.  gard.py:205-212
 template <int P, typename XF, typename EF>
-__device__ double logistic_prob_class0(int k, int p, const XF& xv, const EF& exceeds, const double (&xq)[P], double Creg) {
+__device__ void logistic_fit(int k, int p, const XF& xv, const EF& exceeds, double Creg, double (&th)[P + 1]) {
     constexpr int D = P + 1;
-    double th[D];
 #pragma unroll
     for (int f = 0; f < D; ++f) th[f] = 0.0;
     const double lam = 1.0 / Creg;
@@ -269,6 +268,12 @@ __device__ double logistic_prob_class0(int k, int p, const XF& xv, const EF& exc
         fcur = fnew;
         if (dmax < 1e-14 * tmax) break;
     }
+}
+
+template <int P, typename XF, typename EF>
+__device__ double logistic_prob_class0(int k, int p, const XF& xv, const EF& exceeds, const double (&xq)[P], double Creg) {
+    double th[P + 1];
+    logistic_fit<P>(k, p, xv, exceeds, Creg, th);
     double z = th[P];
 #pragma unroll
     for (int f = 0; f < P; ++f) if (f < p) z += th[f] * xq[f];
@@ -665,9 +670,232 @@ static int dispatch_analog(const AnalogParams& a, cudaStream_t st) {
     }
 }
 
+// ---------------------------------------------------------------- PureRegression (gard.py:367-504)
+// One thread per cell (rows coalesced across cells): centred normal equations of the rows above the
+// threshold accumulated in float64 over the whole training window → Cholesky (Jacobi minimum-norm
+// when rank deficient) → in-sample RMSE; with a threshold the logistic exceedance model of ALL rows by
+// damped Newton (one pass over the window per evaluation).  model[c * MODEL_LD + ...]:
+//   [0..P) beta, [P] intercept, [P+1] rmse, [P+2..2P+2) logistic weights, [2P+2] logistic intercept,
+//   [2P+3] status: 0 = two classes, 1 = no threshold / every row exceeds (prob = 1), 2 = no row exceeds
+constexpr int PR_MODEL_LD = 2 * AN_PMAX + 4;
+
+template <typename T, int P>
+__global__ void pure_regression_fit_kernel(const T* __restrict__ X, const T* __restrict__ y, int64_t ld, int64_t C,
+                                           int t_fit, int p_rt, int has_thresh, double thresh, double logistic_c,
+                                           double* __restrict__ model, const uint8_t* __restrict__ valid,
+                                           int32_t* __restrict__ nonfinite) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double* mo = model + c * PR_MODEL_LD;
+    if (valid && !valid[c]) { for (int i = 0; i < PR_MODEL_LD; ++i) mo[i] = NAN; return; }
+    const int p = (P == AN_PMAX) ? p_rt : P;
+    const T th = (T)thresh;
+    auto xv = [&](int i, int f) -> double { return (double)X[((int64_t)i * p + f) * ld + c]; };
+    auto yraw = [&](int i) -> T { return y[(int64_t)i * ld + c]; };
+    auto use = [&](int i) -> bool { return !has_thresh || (yraw(i) > th); };
+    int m = 0;
+    double xm[P], ym = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int f = 0; f < P; ++f) xm[f] = 0.0;
+    for (int i = 0; i < t_fit; ++i) {
+        const double yi = (double)yraw(i);
+        bad |= !isfinite(yi);
+        const bool u = use(i);
+        m += u ? 1 : 0;
+        if (u) ym += yi;
+#pragma unroll
+        for (int f = 0; f < P; ++f) if (f < p) { const double x = xv(i, f); bad |= !isfinite(x); if (u) xm[f] += x; }
+    }
+    if (bad && nonfinite) atomicOr(nonfinite, 1);
+    double status = (has_thresh && m < t_fit) ? 0.0 : 1.0;
+    if (m == 0) {                                   // gard.py:435: LinearRegression on an empty selection raises — bit 2
+        if (nonfinite) atomicOr(nonfinite, 4);
+        for (int i = 0; i < PR_MODEL_LD; ++i) mo[i] = NAN;
+        mo[2 * P + 3] = 2.0;
+        return;
+    }
+    ym /= (double)m;
+#pragma unroll
+    for (int f = 0; f < P; ++f) xm[f] /= (double)m;
+    double A[P][P], b[P];
+#pragma unroll
+    for (int f = 0; f < P; ++f) { b[f] = 0.0;
+#pragma unroll
+        for (int g = 0; g < P; ++g) A[f][g] = 0.0; }
+    for (int i = 0; i < t_fit; ++i) {
+        if (!use(i)) continue;
+        double dx[P];
+#pragma unroll
+        for (int f = 0; f < P; ++f) dx[f] = (f < p) ? xv(i, f) - xm[f] : 0.0;
+        const double dy = (double)yraw(i) - ym;
+#pragma unroll
+        for (int f = 0; f < P; ++f) { b[f] += dx[f] * dy;
+#pragma unroll
+            for (int g = 0; g <= f; ++g) A[f][g] += dx[f] * dx[g]; }
+    }
+    double beta[P];
+    bool solved = false;
+    if (m <= p) { sym_minnorm_solve<P>(A, b, p, beta); solved = true; }
+    if (!solved) {
+        bool live[P];
+        bool deficient = false;
+        double L[P][P];
+#pragma unroll
+        for (int f = 0; f < P; ++f) {
+            live[f] = f < p;
+#pragma unroll
+            for (int g = 0; g <= f; ++g) {
+                double sacc = A[f][g];
+#pragma unroll
+                for (int h = 0; h < g; ++h) sacc -= L[f][h] * L[g][h];
+                if (g == f) {
+                    if (live[f] && !(sacc > 1e-13 * A[f][f])) deficient = true;
+                    if (!(sacc > 0.0) || !live[f]) { live[f] = false; L[f][f] = 1.0; } else L[f][f] = sqrt(sacc);
+                } else {
+                    L[f][g] = live[g] ? sacc / L[g][g] : 0.0;
+                }
+            }
+        }
+        if (deficient) {
+            sym_minnorm_solve<P>(A, b, p, beta);       // collinear predictors: lstsq's minimum-norm answer
+        } else {
+#pragma unroll
+            for (int f = 0; f < P; ++f) {
+                double sacc = b[f];
+#pragma unroll
+                for (int h = 0; h < f; ++h) sacc -= L[f][h] * beta[h];
+                beta[f] = live[f] ? sacc / L[f][f] : 0.0;
+            }
+#pragma unroll
+            for (int f = P - 1; f >= 0; --f) {
+                double sacc = beta[f];
+#pragma unroll
+                for (int h = f + 1; h < P; ++h) sacc -= L[h][f] * beta[h];
+                beta[f] = live[f] ? sacc / L[f][f] : 0.0;
+            }
+        }
+    }
+    double icpt = ym;
+#pragma unroll
+    for (int f = 0; f < P; ++f) icpt -= xm[f] * beta[f];
+    double sse = 0.0;
+    for (int i = 0; i < t_fit; ++i) {
+        if (!use(i)) continue;
+        double yh = icpt;
+#pragma unroll
+        for (int f = 0; f < P; ++f) if (f < p) yh += xv(i, f) * beta[f];
+        const double r = (double)yraw(i) - yh;
+        sse += r * r;
+    }
+#pragma unroll
+    for (int f = 0; f < P; ++f) mo[f] = beta[f];
+    mo[P] = icpt;
+    mo[P + 1] = sqrt(sse / (double)m);
+    mo[2 * P + 3] = status;
+    if (status == 0.0) {
+        // logistic exceedance model of ALL rows (gard.py:417): the Newton solver of the analog epilogue
+        double w[P + 1];
+        logistic_fit<P>(t_fit, p, xv, use, logistic_c, w);
+#pragma unroll
+        for (int f = 0; f <= P; ++f) mo[P + 2 + f] = w[f];
+    } else {
+#pragma unroll
+        for (int f = 0; f <= P; ++f) mo[P + 2 + f] = 0.0;
+    }
+}
+
+template <typename T, int P>
+__global__ void pure_regression_predict_kernel(const T* __restrict__ Xq, int64_t ld, int64_t C, int t_query, int p_rt,
+                                               const double* __restrict__ model, void* __restrict__ out, int out_f64,
+                                               int64_t ld_out, const uint8_t* __restrict__ valid,
+                                               int32_t* __restrict__ nonfinite) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (c >= C || q >= t_query) return;
+    const int p = (P == AN_PMAX) ? p_rt : P;
+    const int64_t base = (int64_t)q * 3 * ld_out + c;
+    double pred = NAN, prob = NAN, err = NAN;
+    if (!valid || valid[c]) {
+        const double* mo = model + c * PR_MODEL_LD;
+        pred = mo[P];
+        double z = mo[2 * P + 2];
+#pragma unroll
+        for (int f = 0; f < P; ++f) {
+            if (f < p) {
+                const double x = (double)Xq[((int64_t)q * p + f) * ld + c];
+                if (nonfinite && !isfinite(x)) atomicOr(nonfinite, 1);
+                pred += x * mo[f];
+                z += x * mo[P + 2 + f];
+            }
+        }
+        err = mo[P + 1];
+        prob = (mo[2 * P + 3] == 0.0) ? 1.0 / (1.0 + exp(-z)) : 1.0;      // predict_proba[:, 1]   gard.py:467
+    }
+    if (out_f64) { double* o = (double*)out; o[base] = pred; o[base + ld_out] = prob; o[base + 2 * ld_out] = err; }
+    else { float* o = (float*)out; o[base] = (float)pred; o[base + ld_out] = (float)prob; o[base + 2 * ld_out] = (float)err; }
+}
+
+template <typename T, int P>
+static int launch_pure_regression_fit(const T* X, const T* y, int64_t ld, int64_t C, int t_fit, int p, int has_thresh,
+                                      double thresh, double logistic_c, double* model, const uint8_t* valid,
+                                      int32_t* nonfinite, cudaStream_t st) {
+    pure_regression_fit_kernel<T, P><<<(unsigned)((C + 63) / 64), 64, 0, st>>>(X, y, ld, C, t_fit, p, has_thresh, thresh, logistic_c, model, valid, nonfinite);
+    SDB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+template <typename T, int P>
+static int launch_pure_regression_predict(const T* Xq, int64_t ld, int64_t C, int t_query, int p, const double* model,
+                                          void* out, int out_f64, int64_t ld_out, const uint8_t* valid,
+                                          int32_t* nonfinite, cudaStream_t st) {
+    dim3 grid((unsigned)((C + 127) / 128), (unsigned)t_query);
+    pure_regression_predict_kernel<T, P><<<grid, 128, 0, st>>>(Xq, ld, C, t_query, p, model, out, out_f64, ld_out, valid, nonfinite);
+    SDB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace sdb
 
 using namespace sdb;
+
+#define SDB_PR_DISPATCH(FN, T, ...)                                             \
+    switch (n_features) {                                                       \
+        case 1: return FN<T, 1>(__VA_ARGS__);                                   \
+        case 2: return FN<T, 2>(__VA_ARGS__);                                   \
+        case 3: return FN<T, 3>(__VA_ARGS__);                                   \
+        case 4: return FN<T, 4>(__VA_ARGS__);                                   \
+        default: return FN<T, AN_PMAX>(__VA_ARGS__);                            \
+    }
+
+extern "C" int sdb_pure_regression_model_ld(void) { return PR_MODEL_LD; }
+
+extern "C" int sdb_pure_regression_fit(const void* X_train, const void* y_train, int dtype, int64_t ld, int64_t n_cells,
+                                       int t_fit, int n_features, int has_thresh, double thresh, double logistic_c,
+                                       double* model, const uint8_t* cell_valid, int32_t* nonfinite, void* stream) {
+    if (!X_train || !y_train || !model) return sdb_fail(SDB_E_INVALID, "sdb_pure_regression_fit: NULL pointer");
+    if (n_cells <= 0 || t_fit <= 0 || ld < n_cells) return sdb_fail(SDB_E_INVALID, "sdb_pure_regression_fit: bad shape");
+    if (n_features < 1 || n_features > AN_PMAX) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_pure_regression_fit: 1..%d predictors supported, got %d", AN_PMAX, n_features);
+    if (has_thresh && !(logistic_c > 0.0)) return sdb_fail(SDB_E_INVALID, "sdb_pure_regression_fit: logistic_c must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SDB_F32) { SDB_PR_DISPATCH(launch_pure_regression_fit, float, (const float*)X_train, (const float*)y_train, ld, n_cells, t_fit, n_features, has_thresh, thresh, logistic_c, model, cell_valid, nonfinite, st) }
+    if (dtype == SDB_F64) { SDB_PR_DISPATCH(launch_pure_regression_fit, double, (const double*)X_train, (const double*)y_train, ld, n_cells, t_fit, n_features, has_thresh, thresh, logistic_c, model, cell_valid, nonfinite, st) }
+    return sdb_fail(SDB_E_INVALID, "sdb_pure_regression_fit: bad dtype %d", dtype);
+}
+
+extern "C" int sdb_pure_regression_predict(const void* X_query, int dtype, int64_t ld, int64_t n_cells, int t_query,
+                                           int n_features, const double* model, void* out, int out_dtype, int64_t ld_out,
+                                           const uint8_t* cell_valid, int32_t* nonfinite, void* stream) {
+    if (!X_query || !model || !out) return sdb_fail(SDB_E_INVALID, "sdb_pure_regression_predict: NULL pointer");
+    if (n_cells <= 0 || t_query <= 0 || ld < n_cells || ld_out < n_cells) return sdb_fail(SDB_E_INVALID, "sdb_pure_regression_predict: bad shape");
+    if (t_query > 65535) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_pure_regression_predict: at most 65535 query steps per call");
+    if (n_features < 1 || n_features > AN_PMAX) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_pure_regression_predict: 1..%d predictors supported, got %d", AN_PMAX, n_features);
+    if (out_dtype != SDB_F32 && out_dtype != SDB_F64) return sdb_fail(SDB_E_INVALID, "sdb_pure_regression_predict: bad out dtype");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int of64 = out_dtype == SDB_F64;
+    if (dtype == SDB_F32) { SDB_PR_DISPATCH(launch_pure_regression_predict, float, (const float*)X_query, ld, n_cells, t_query, n_features, model, out, of64, ld_out, cell_valid, nonfinite, st) }
+    if (dtype == SDB_F64) { SDB_PR_DISPATCH(launch_pure_regression_predict, double, (const double*)X_query, ld, n_cells, t_query, n_features, model, out, of64, ld_out, cell_valid, nonfinite, st) }
+    return sdb_fail(SDB_E_INVALID, "sdb_pure_regression_predict: bad dtype %d", dtype);
+}
 
 extern "C" int sdb_analog_predict(int kind, const void* X_train, const void* y_train, const void* X_query,
                                   int dtype, int64_t ld, int64_t n_cells,

@@ -435,3 +435,38 @@ def qm_predict_detrended(st_raw: QMFitted, st_res: QMFitted, icpt_fit: torch.Ten
                                     _code(climo) if climo is not None else _lib.SDB_F32, C, int(bool(return_anoms)),
                                     _ptr(out), _TORCH_CODE[od], C, _ptr(valid), _stream()), 'sdb_bcsd_combine')
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# PureRegression (gard.py:367-504)
+# ---------------------------------------------------------------------------------------------
+def pure_regression_fit(X_train: torch.Tensor, y_train: torch.Tensor, *, thresh=None, logistic_C: float = 1.0,
+                        valid=None, nonfinite=None) -> torch.Tensor:
+    """One OLS (+ logistic exceedance model) per cell → model ``[C, model_ld]`` float64 (library-private layout)."""
+    lib = _lib.load()
+    X_train, y_train = X_train.contiguous(), y_train.contiguous()
+    T, p, C = X_train.shape
+    if y_train.shape != (T, C) or y_train.dtype != X_train.dtype:
+        raise ValueError('X_train [T, p, C] and y_train [T, C] must agree in shape and dtype')
+    model = torch.empty((C, lib.sdb_pure_regression_model_ld()), dtype=torch.float64, device=X_train.device)
+    _lib.check(lib.sdb_pure_regression_fit(_ptr(X_train), _ptr(y_train), _code(X_train), C, C, T, p,
+                                           int(thresh is not None), float(thresh) if thresh is not None else 0.0,
+                                           float(logistic_C), _ptr(model), _ptr(valid), _ptr(nonfinite), _stream()),
+               'sdb_pure_regression_fit')
+    return model
+
+
+def pure_regression_predict(model: torch.Tensor, X_query: torch.Tensor, *, out_dtype=None, valid=None,
+                            nonfinite=None) -> torch.Tensor:
+    lib = _lib.load()
+    X_query = X_query.contiguous()
+    Tq, p, C = X_query.shape
+    od = out_dtype or X_query.dtype
+    out = torch.empty((Tq, 3, C), dtype=od, device=X_query.device)
+    step = 65535                                     # query steps per launch (grid.y)
+    for q0 in range(0, Tq, step):
+        q1 = min(Tq, q0 + step)
+        _lib.check(lib.sdb_pure_regression_predict(_ptr(X_query[q0:q1]), _code(X_query), C, C, q1 - q0, p, _ptr(model),
+                                                   _ptr(out[q0:q1]), _TORCH_CODE[od], C, _ptr(valid), _ptr(nonfinite),
+                                                   _stream()), 'sdb_pure_regression_predict')
+    return out

@@ -1,12 +1,12 @@
 """Drop-in surface of ``skdownscale.pointwise_models`` for the B200 hot path
 (skdownscale/pointwise_models/__init__.py:1-36).  Estimators outside the hot path
-(PureRegression, ZScoreRegressor, ...) are not provided; QuantileMappingReressor and
+(ZScoreRegressor, GroupedRegressor, ...) are not provided; QuantileMappingReressor and
 EquidistantCdfMatcher are the first "next" row of SURVEY.md §8(f).
 """
 
 from .bcsd import BcsdPrecipitation, BcsdTemperature
 from .core import PointWiseDownscaler
-from .gard import AnalogRegression, PureAnalog
+from .gard import AnalogRegression, PureAnalog, PureRegression
 from .groupers import DAY_GROUPER, MONTH_GROUPER, PaddedDOYGrouper
 from .quantile import EquidistantCdfMatcher, QuantileMapper, QuantileMappingReressor
 
@@ -16,6 +16,7 @@ __all__ = [
     'PointWiseDownscaler',
     'AnalogRegression',
     'PureAnalog',
+    'PureRegression',
     'DAY_GROUPER',
     'MONTH_GROUPER',
     'PaddedDOYGrouper',

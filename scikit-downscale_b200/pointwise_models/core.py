@@ -23,7 +23,7 @@ import torch
 from .. import engine
 from .base import cuda_device
 from .bcsd import BcsdBase
-from .gard import AnalogBase
+from .gard import AnalogBase, PureRegression
 from .quantile import QuantileMapper, QuantileMappingReressor
 
 try:  # xarray is optional (absent in the build container)
@@ -71,7 +71,7 @@ class PointWiseDownscaler:
 
     # ------------------------------------------------------------------ input handling
     def _multi_feature(self):
-        return isinstance(self._model, AnalogBase)
+        return isinstance(self._model, (AnalogBase, PureRegression))
 
     def _to_block(self, X, feature_dim, time=None) -> _Block:
         """core.py:427-440 (_to_feature_x) + core.py:40-66 (_da_to_df) for a whole block."""
@@ -173,7 +173,7 @@ class PointWiseDownscaler:
                 if by.index is not None:
                     pd.testing.assert_index_equal(pd.Index(bx.index), pd.Index(by.index))   # base.py:17
                 model.fit_batched(x[:, 0], y[:, 0], bx.index, valid=valid)
-            elif isinstance(model, AnalogBase):
+            elif isinstance(model, (AnalogBase, PureRegression)):
                 model.fit_batched(x, y[:, 0], valid=valid)
             elif isinstance(model, QuantileMappingReressor):
                 if x.shape[1] != 1:

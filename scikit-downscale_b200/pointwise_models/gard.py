@@ -172,3 +172,84 @@ class PureAnalog(AnalogBase):
                 if ok[c]:
                     rand_idx[:, c] = np.random.randint(low=0, high=k, size=Tq)
         return self._run(_KINDS[kind], k, X, out_dtype, thresh=self.thresh, rand_idx=rand_idx, want_idx=want_idx)
+
+
+class PureRegression(RegressorMixin, BaseEstimator):
+    """PureRegression (gard.py:367-504): one linear regression per cell over the whole training window
+    (the rows above ``thresh`` when given), ``exceedance_prob`` = P(exceed) of a logistic regression on
+    all rows, ``prediction_error`` = the in-sample RMSE."""
+
+    _fit_attributes = ['logistic_model_', 'linear_model_', 'fit_error_']
+    n_outputs = 3
+    output_names = ['pred', 'exceedance_prob', 'prediction_error']
+
+    def __init__(self, thresh=None, logistic_kwargs=None, linear_kwargs=None):
+        self.thresh = thresh
+        self.logistic_kwargs = logistic_kwargs
+        self.linear_kwargs = linear_kwargs
+
+    def fit_batched(self, X: torch.Tensor, y: torch.Tensor, valid=None):
+        """X ``[T, p, C]``, y ``[T, C]`` CUDA tensors."""
+        C_reg = 1.0
+        for k, v in default_none_kwargs(self.logistic_kwargs).items():
+            if k == 'C':
+                C_reg = float(v)
+            elif k not in ('tol', 'max_iter', 'n_jobs', 'verbose', 'random_state', 'warm_start'):
+                raise NotImplementedError(f'logistic_kwargs {k}={v!r} is not supported on the B200 path')
+        for k, v in default_none_kwargs(self.linear_kwargs).items():
+            if not ((k == 'fit_intercept' and v) or k in ('copy_X', 'n_jobs', 'tol') or (k == 'positive' and not v)):
+                raise NotImplementedError(f'linear_kwargs {k}={v!r} is not supported on the B200 path')
+        self._valid = valid
+        self._nonfinite = torch.zeros(1, dtype=torch.int32, device=X.device)
+        self._dtype = X.dtype
+        self._model = engine.pure_regression_fit(X, y, thresh=self.thresh, logistic_C=C_reg, valid=valid,
+                                                 nonfinite=self._nonfinite)
+        self.n_features_in_ = X.shape[1]
+        return self
+
+    def check_fit(self):
+        self._check_finite()
+
+    def _check_finite(self):
+        flags = int(self._nonfinite.item())
+        if flags:
+            self._nonfinite.zero_()
+            if flags & 1:
+                raise ValueError('Input contains NaN or infinity.')
+            # gard.py:435: no row above thresh → LinearRegression.fit on an empty selection
+            raise ValueError(f'Found array with 0 sample(s) (shape=(0, {self.n_features_in_})) while a minimum of 1 '
+                             'is required by LinearRegression.')
+
+    def predict_batched(self, X: torch.Tensor, out_dtype=None, **_):
+        if not hasattr(self, '_model'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
+                                 "appropriate arguments before using this estimator.")
+        if X.shape[1] != self.n_features_in_:
+            raise ValueError(f'X has {X.shape[1]} features, but {self.__class__.__name__} is expecting '
+                             f'{self.n_features_in_} features as input.')
+        if X.dtype != self._dtype:
+            X = X.to(self._dtype)
+        return engine.pure_regression_predict(self._model, X, out_dtype=out_dtype, valid=self._valid,
+                                              nonfinite=self._nonfinite)
+
+    # ---- per-cell API of the reference
+    def fit(self, X, y):
+        dev = cuda_device()
+        x_t, _, _ = series_to_device(X, dev)
+        y_t, _, _ = series_to_device(y, dev)
+        if y_t.shape[1] != 1:
+            raise ValueError('y should be a 1d array or a column vector')
+        if x_t.dtype != y_t.dtype:
+            x_t, y_t = x_t.to(torch.float64), y_t.to(torch.float64)
+        self.fit_batched(x_t.unsqueeze(-1), y_t)
+        self._check_finite()
+        self.fit_error_ = float(self._model[0, self.n_features_in_ + 1 if self.n_features_in_ <= 4 else 9].item())
+        return self
+
+    def predict(self, X):
+        return_df = isinstance(X, pd.DataFrame)
+        x_t, _, _ = series_to_device(X, cuda_device())
+        out = self.predict_batched(x_t.unsqueeze(-1), out_dtype=torch.float64)
+        self._check_finite()
+        out = out[:, :, 0].cpu().numpy()
+        return pd.DataFrame(out, columns=self.output_names) if return_df else out

@@ -308,6 +308,29 @@ def main():
     ar_thresh_case('analogreg_thresh_k10_C', 300, 160, 54, 10, -0.8, C_reg=0.3)
     ar_thresh_case('analogreg_thresh_k200', 400, 60, 53, 200, 0.0)
 
+    # --- 7. PureRegression: one OLS (+ logistic exceedance model) per cell
+    PureRegression = ref['gard'].PureRegression
+
+    def pr_case(name, T, Tq, C, seed, thresh=None, dtype=np.float32, p=3):
+        Xtr, ytr, Xq = synth.analog(T, Tq, C, p, seed, dtype=dtype)
+        out = np.empty((Tq, 3, C), dtype=np.float64)
+        tight = np.empty((Tq, C), dtype=np.float64)
+        for c in range(C):
+            m = PureRegression(thresh=thresh).fit(_df(Xtr[..., c]), _df(ytr[:, c]))
+            out[:, :, c] = np.asarray(m.predict(_df(Xq[..., c])), dtype=np.float64)
+            if thresh is not None:
+                mt = PureRegression(thresh=thresh, logistic_kwargs={'tol': 1e-12, 'max_iter': 10000})
+                mt.fit(_df(Xtr[..., c].astype(np.float64)), _df(ytr[:, c].astype(np.float64)))
+                tight[:, c] = np.asarray(mt.predict(_df(Xq[..., c].astype(np.float64))))[:, 1]
+        kw = dict(Xtr=Xtr, ytr=ytr, Xq=Xq, out=out)
+        if thresh is not None:
+            kw.update(prob_tight=tight, thresh=np.float64(thresh))
+        save(name, **kw)
+
+    pr_case('pure_regression', 600, 150, 3, 61)
+    pr_case('pure_regression_thresh', 600, 150, 2, 62, thresh=0.0)
+    pr_case('pure_regression_f64_thresh', 500, 120, 2, 63, thresh=-0.3, dtype=np.float64, p=2)
+
     import sklearn
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump({'numpy': np.__version__, 'pandas': pd.__version__, 'sklearn': sklearn.__version__,

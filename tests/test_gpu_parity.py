@@ -598,6 +598,43 @@ def test_analog_regression_thresh_one_class_raises(dev):
         m.predict(pd.DataFrame(Xq[..., 0]))
 
 
+@pytest.mark.parametrize('name', ['pure_regression', 'pure_regression_thresh', 'pure_regression_f64_thresh'])
+def test_pure_regression_golden(dev, golden, name):
+    """PureRegression (gard.py:367-504): prediction and RMSE to 1e-5 of the target spread (the reference
+    fits float32 inputs in float32), 1e-9 for float64 inputs; exceedance probability 1e-6 against the
+    tightly converged reference and 2e-3 against its default lbfgs run."""
+    g = golden(name)
+    th = float(g['thresh']) if 'thresh' in g else None
+    f64 = g['Xtr'].dtype == np.float64
+    pw = pm().PointWiseDownscaler(pm().PureRegression(thresh=th))
+    pw.fit(g['Xtr'], g['ytr'])
+    got = pw.predict(g['Xq'])
+    assert got.shape == g['out'].shape and got.dtype == g['Xq'].dtype
+    tol = 1e-9 if f64 else 1e-5 * np.std(g['ytr'])
+    np.testing.assert_allclose(got[:, [0, 2]], g['out'][:, [0, 2]], rtol=0, atol=tol)
+    if th is None:
+        assert (got[:, 1] == 1.0).all()
+    else:
+        np.testing.assert_allclose(got[:, 1], g['prob_tight'], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(got[:, 1], g['out'][:, 1], rtol=0, atol=2e-3)
+    # per-cell estimator API
+    m = pm().PureRegression(thresh=th).fit(pd.DataFrame(g['Xtr'][..., 0]), pd.DataFrame(g['ytr'][:, 0]))
+    o = m.predict(pd.DataFrame(g['Xq'][..., 0]))
+    assert list(o.columns) == ['pred', 'exceedance_prob', 'prediction_error']
+    np.testing.assert_allclose(o.values[:, [0, 2]], g['out'][:, [0, 2], 0], rtol=0, atol=tol)
+    want = oracle.pure_regression_fit_predict(g['Xtr'][..., 0].astype(np.float64), g['ytr'][:, 0].astype(np.float64),
+                                              g['Xq'][..., 0].astype(np.float64), th)
+    np.testing.assert_allclose(o.values, want, rtol=1e-9, atol=1e-9)       # the float64 arithmetic itself
+    assert abs(m.fit_error_ - want[0, 2]) <= 1e-9
+
+
+def test_pure_regression_no_exceeding_row_raises(dev):
+    Xtr, ytr, Xq = synth.analog(100, 10, 2, 3, seed=8)
+    pw = pm().PointWiseDownscaler(pm().PureRegression(thresh=1e9))
+    with pytest.raises(ValueError, match='0 sample'):                    # gard.py:435
+        pw.fit(Xtr, ytr)
+
+
 @pytest.mark.parametrize('p,k,T,Tq', [(1, 5, 700, 300), (3, 10, 2500, 600), (3, 16, 1100, 257), (3, 17, 900, 100),
                                       (4, 10, 1030, 90), (6, 8, 600, 70), (3, 200, 1500, 64)])
 def test_analog_indices_bit_exact(dev, p, k, T, Tq):

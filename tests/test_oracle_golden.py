@@ -244,3 +244,23 @@ def test_qm_detrend(golden, name):
         _close(oracle.quantile_mapper_transform_detrend(g['Xp'][:, c], st), g['out'][:, c], rtol=1e-12, atol=1e-12)
     out = oracle.pointwise_fit_predict({'name': 'QuantileMapper', 'detrend': True}, None, g['ytr'], g['Xp'])
     _close(out, g['out'].astype(g['Xp'].dtype), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['pure_regression', 'pure_regression_thresh', 'pure_regression_f64_thresh'])
+def test_pure_regression(golden, name):
+    """PureRegression (gard.py:367-504) against the live reference.  float32 inputs are fitted in float32 by
+    the reference (LAPACK sgelsd): agreement to 1e-5 of the target spread; float64 inputs: 1e-9.  The
+    exceedance probability: 1e-7 against the tightly converged reference, 2e-3 against its default lbfgs run."""
+    g = golden(name)
+    th = float(g['thresh']) if 'thresh' in g else None
+    f64 = g['Xtr'].dtype == np.float64
+    for c in range(g['Xq'].shape[-1]):
+        o = oracle.pure_regression_fit_predict(g['Xtr'][..., c], g['ytr'][:, c], g['Xq'][..., c], th)
+        ref = g['out'][:, :, c]
+        tol = 1e-9 if f64 else 1e-5 * np.std(g['ytr'][:, c])
+        _close(o[:, [0, 2]], ref[:, [0, 2]], rtol=0, atol=tol)
+        if th is None:
+            assert (o[:, 1] == 1.0).all() and (ref[:, 1] == 1.0).all()
+        else:
+            _close(o[:, 1], g['prob_tight'][:, c], rtol=0, atol=1e-7)
+            _close(o[:, 1], ref[:, 1], rtol=0, atol=2e-3)

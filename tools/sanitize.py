@@ -13,8 +13,8 @@ import synth
 import skdownscale_b200  # noqa
 from skdownscale_b200 import _lib, engine
 from skdownscale_b200.pointwise_models import (AnalogRegression, BcsdPrecipitation, BcsdTemperature,
-                                               EquidistantCdfMatcher, PureAnalog, QuantileMapper,
-                                               QuantileMappingReressor)
+                                               EquidistantCdfMatcher, PureAnalog, PureRegression,
+                                               QuantileMapper, QuantileMappingReressor)
 
 dev = torch.device('cuda:0')
 T, C = 1200, 11
@@ -45,6 +45,9 @@ for m in (PureAnalog(n_analogs=10, kind='weight_analogs'), AnalogRegression(n_an
 m = AnalogRegression(n_analogs=12, thresh=-0.5)
 m.fit_batched(engine.as_device(A, dev), engine.as_device(ya, dev))
 m.predict_batched(engine.as_device(Aq, dev))
+for m in (PureRegression(), PureRegression(thresh=0.0)):
+    m.fit_batched(engine.as_device(A, dev), engine.as_device(ya, dev))
+    m.predict_batched(engine.as_device(Aq, dev))
 # CDF-to-CDF regressors, every tail mode; detrending mappers; non-default Cunnane tails
 for ex in (None, 'min', 'max', 'both', '1to1'):
     for est in (QuantileMappingReressor(extrapolate=ex, n_endpoints=5), EquidistantCdfMatcher(kind='ratio', extrapolate=ex, n_endpoints=5)):
