@@ -197,6 +197,7 @@ class BcsdBase(TimeSynchronousDownscaler):
                                  "appropriate arguments before using this estimator.")
         if self.timestep == 'daily' and self.return_anoms:
             raise ValueError('shape of climo is not equal to input array')
+        self._no_detrend_streaming()
         st = self._state
         dev = st.sorted_state.device
         Xh = self._host2d(X, 'X')
