@@ -40,6 +40,7 @@ from .quantile import (  # noqa: F401
     quantile_mapper_transform,
     quantile_mapper_transform_detrend,
     rank_max_ties,
+    trend_aware_qm_fit_predict,
 )
 from .bcsd import (  # noqa: F401
     bcsd_precipitation_fit,

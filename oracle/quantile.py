@@ -277,3 +277,32 @@ def qmr_well_conditioned(st: dict, X: np.ndarray, estimator: str) -> np.ndarray:
         if upper:
             ok &= q <= st['x_pp'][-2]
     return ok
+
+
+def trend_aware_qm_fit_predict(X_train, y_train, X_pred, extrapolate=None, n_endpoints: int = 10) -> np.ndarray:
+    """TrendAwareQuantileMappingRegressor(QuantileMappingReressor(extrapolate, n_endpoints)) for ONE cell
+    (quantile.py:639-716; the default LinearTrendTransformer — passing another one leaves the attribute
+    unset in the reference, quantile.py:655-656).  NOT yet in the product: pinned here for the next round.
+
+    fit: remove the linear trends of X and y (each its own), fit the CDF-to-CDF regressor on the
+    residuals; predict: remove the new X's trend, map the residuals, add the new trend line centred at
+    zero plus ``(mean(X_new) - mean(X_fit)) + mean(y_fit)`` (column means in the input dtype, like
+    DataFrame.mean).  Returns float64 [n, 1] like the reference."""
+    Xf = np.asarray(X_train).reshape(-1)
+    yf = np.asarray(y_train).reshape(-1)
+    Xp = np.asarray(X_pred).reshape(-1)
+
+    def detrended(v):
+        slope, icpt = linear_trend_fit(v)
+        line = np.arange(len(v)) * slope + icpt
+        return v - line, line
+
+    x_res, _ = detrended(Xf)
+    y_res, _ = detrended(yf)
+    st = qm_regressor_fit(x_res, y_res, extrapolate, n_endpoints)
+    xp_res, line = detrended(Xp)
+    y_hat = qm_regressor_predict(st, xp_res).reshape(-1, 1).astype(np.float64)
+    col_mean = lambda a: a.mean(dtype=np.float64).astype(a.dtype)      # noqa: E731  pandas: float64 accumulate, cast back
+    delta = (col_mean(Xp) - col_mean(Xf)) + col_mean(yf)
+    centred = line - line.mean()
+    return y_hat + (centred.reshape(-1, 1) + delta)

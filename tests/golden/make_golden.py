@@ -156,6 +156,26 @@ def main():
     qmr_case('qmr_pred_longer_shifted', 500, 1200, 2, 18, offset=1.5)      # values beyond both ends of the fitted range
     qmr_case('qmr_f64_shorter', 900, 400, 2, 19, dtype=np.float64, ne=10)
 
+    # TrendAwareQuantileMappingRegressor over the regressor above (quantile.py:639-716): pinned for the
+    # oracle only — the estimator is not in the product yet
+    TAQ = ref['quantile'].TrendAwareQuantileMappingRegressor
+
+    def taq_case(name, Tf, Tp, C, seed, dtype=np.float32):
+        Xtr, ytr, _ = synth.temperature(Tf, C, seed, dtype)
+        _, _, Xp = synth.temperature(Tp, C, seed + 100, dtype)
+        Xp = (Xp + np.linspace(0, 4, Tp)[:, None]).astype(dtype)
+        arrays = dict(Xtr=Xtr, ytr=ytr, Xp=Xp)
+        for ex in (None, '1to1'):
+            out = np.empty((Tp, C), dtype=np.float64)
+            for c in range(C):
+                m = TAQ(QMR(extrapolate=ex, n_endpoints=6)).fit(pd.DataFrame(Xtr[:, c]), pd.DataFrame(ytr[:, c]))
+                out[:, c] = m.predict(pd.DataFrame(Xp[:, c]))[:, 0]
+            arrays['out_none' if ex is None else 'out_1to1'] = out
+        save(name, **arrays)
+
+    taq_case('trend_aware_qmr', 800, 1100, 2, 70)
+    taq_case('trend_aware_qmr_f64', 500, 400, 2, 71, dtype=np.float64)
+
     # the reference's own known-answer test (test_pointwise_models.py:323-344)
     xs = np.arange(1, 22)
     ka = {}

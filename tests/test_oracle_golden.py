@@ -264,3 +264,14 @@ def test_pure_regression(golden, name):
         else:
             _close(o[:, 1], g['prob_tight'][:, c], rtol=0, atol=1e-7)
             _close(o[:, 1], ref[:, 1], rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize('name', ['trend_aware_qmr', 'trend_aware_qmr_f64'])
+def test_trend_aware_qm_regressor_oracle(golden, name):
+    """TrendAwareQuantileMappingRegressor (quantile.py:639-716) — oracle only (the estimator is a "next"
+    item, not in the product yet): pinned against the live reference so the next round starts from a checker."""
+    g = golden(name)
+    for ex, key in ((None, 'out_none'), ('1to1', 'out_1to1')):
+        for c in range(g['Xp'].shape[1]):
+            o = oracle.trend_aware_qm_fit_predict(g['Xtr'][:, c], g['ytr'][:, c], g['Xp'][:, c], ex, 6)
+            _close(o[:, 0], g[key][:, c], rtol=1e-12, atol=1e-11)
