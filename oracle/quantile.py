@@ -286,7 +286,7 @@ def trend_aware_qm_fit_predict(X_train, y_train, X_pred, extrapolate=None, n_end
 
     fit: remove the linear trends of X and y (each its own), fit the CDF-to-CDF regressor on the
     residuals; predict: remove the new X's trend, map the residuals, add the new trend line centred at
-    zero plus ``(mean(X_new) - mean(X_fit)) + mean(y_fit)`` (column means in the input dtype, like
+    zero plus ``(mean(X_new) - mean(X_fit)) + mean(y_fit)`` (column means summed in the input dtype, like
     DataFrame.mean).  Returns float64 [n, 1] like the reference."""
     Xf = np.asarray(X_train).reshape(-1)
     yf = np.asarray(y_train).reshape(-1)
@@ -302,7 +302,9 @@ def trend_aware_qm_fit_predict(X_train, y_train, X_pred, extrapolate=None, n_end
     st = qm_regressor_fit(x_res, y_res, extrapolate, n_endpoints)
     xp_res, line = detrended(Xp)
     y_hat = qm_regressor_predict(st, xp_res).reshape(-1, 1).astype(np.float64)
-    col_mean = lambda a: a.mean(dtype=np.float64).astype(a.dtype)      # noqa: E731  pandas: float64 accumulate, cast back
+    # DataFrame.mean() of a one-column float32 frame: pandas' nanmean sums in the frame's own dtype (numpy
+    # pairwise summation) and divides by the count — the same value as ndarray.mean() in that dtype
+    col_mean = lambda a: a.sum(dtype=a.dtype) / a.dtype.type(len(a))     # noqa: E731
     delta = (col_mean(Xp) - col_mean(Xf)) + col_mean(yf)
     centred = line - line.mean()
     return y_hat + (centred.reshape(-1, 1) + delta)
