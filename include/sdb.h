@@ -92,7 +92,10 @@ const char* sdb_last_error(void);
 
 /* Testing aid: bit 0 forces the generic (any dtype / any group length) kernels even where the
  * float32 tile kernels apply; bit 1 makes the tile kernels use their 4-byte row accesses (the
- * path rows that are not 16-byte aligned take) everywhere.  Returns the previous flags. */
+ * path rows that are not 16-byte aligned take) everywhere; bits 2 / 3 make sdb_bcsd_fit_predict
+ * sort / rank with the sorting network instead of the counting rank.  Returns the previous flags.
+ * This is the ONE piece of process-wide mutable state in the library (the exception to the
+ * thread-safety paragraph above): set it before issuing work, not concurrently with it. */
 int sdb_set_debug_flags(int flags);
 
 /* Strided host<->device copy of a [height, width_bytes] block (cudaMemcpy2DAsync) on `stream`:
@@ -160,6 +163,34 @@ int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, int64_t n_cel
                    int return_anoms, const int32_t* roll_nbr, const sdb_cunnane_opts* cunnane,
                    void* out, int out_dtype, int64_t ld_out, int32_t* rank_out,
                    const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+/*
+ * fit + predict in ONE pass for the case fit and predict share their time index (same groups, same
+ * lengths — the headline workload): climatologies (sdb_group_mean), then one kernel that sorts the
+ * training group of every cell in shared memory, ranks the prediction group against itself and maps
+ * rank r to the r-th order statistic (n == m: np.interp lands on the knot, quantile.py:523-530) —
+ * the fitted state never travels through HBM.  Results are bit-identical to sdb_qm_fit + sdb_qm_predict.
+ * Replaces  BcsdTemperature.fit + .predict   bcsd.py:197-269
+ *           BcsdPrecipitation.fit + .predict bcsd.py:115-185
+ *           QuantileMapper.fit + .transform  quantile.py:81-147   (mode QM: y_train = the fitted series)
+ *   X_train   [T, ld_train]  only read for mode BCSD_T (x_climo); NULL otherwise
+ *   y_train   [T, ld_train], X_pred [T, ld_pred], out [T, ld_out]; float32 only, groups of <= 1024 steps
+ *             (SDB_E_UNSUPPORTED otherwise: use the split calls)
+ *   x_climo / y_climo  OUTPUTS [n_groups, ld_climo] (y_climo: modes BCSD_*; x_climo: BCSD_T), pandas
+ *             groupby().mean() arithmetic; NULL when the mode does not use them
+ *   sorted_state / state_ld / state_off: optional OUTPUT, the fitted state exactly as sdb_qm_fit writes
+ *             it (so the call leaves a fitted model behind); NULL = not kept
+ *   stats     optional device uint64[8] instrumentation, accumulated: [0] series, [1] / [2] series whose
+ *             training / prediction side took the sorting-network path, [3] / [4] elements that needed
+ *             an exact comparison on the training / prediction side
+ */
+int sdb_bcsd_fit_predict(int mode, const void* X_train, const void* y_train, const void* X_pred, int dtype,
+                         int64_t ld_train, int64_t ld_pred, int64_t n_cells,
+                         const int32_t* rows, const int32_t* len, int n_groups, int max_len,
+                         void* x_climo, void* y_climo, int64_t ld_climo, int return_anoms,
+                         void* sorted_state, int64_t state_ld, const int64_t* state_off,
+                         void* out, int64_t ld_out,
+                         const uint8_t* cell_valid, int32_t* nonfinite, uint64_t* stats, void* stream);
 
 /*
  * Analog downscaling for every cell: exact k-nearest-neighbour search of every query

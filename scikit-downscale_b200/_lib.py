@@ -47,6 +47,13 @@ SIGNATURES = {
                                c_int, c_void_p, c_void_p,
                                c_void_p, c_int, c_int64, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
+    'sdb_bcsd_fit_predict': (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                     c_int64, c_int64, c_int64,
+                                     c_void_p, c_void_p, c_int, c_int,
+                                     c_void_p, c_void_p, c_int64, c_int,
+                                     c_void_p, c_int64, c_void_p,
+                                     c_void_p, c_int64,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
     'sdb_analog_predict': (c_int, [c_int, c_void_p, c_void_p, c_void_p,
                                    c_int, c_int64, c_int64,
                                    c_int, c_int, c_int, c_int,

@@ -9,6 +9,7 @@ namespace sdb {
 
 char* sdb_error_buffer();           // thread-local, defined in sdb_api.cu
 constexpr int kErrLen = 512;
+extern int g_debug_flags;           // defined in sdb_api.cu (sdb_set_debug_flags)
 
 inline int sdb_fail(int code, const char* fmt, ...) {
     va_list ap;

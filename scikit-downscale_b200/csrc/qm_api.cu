@@ -55,13 +55,10 @@ static int pick_np(int max_len) {
     return -1;
 }
 
-static int g_debug_flags = 0;      // bit 0: force the generic kernels; bit 1: tile kernels without 16-byte row accesses (testing)
 
 }  // namespace sdb
 
 using namespace sdb;
-
-extern "C" int sdb_set_debug_flags(int flags) { int old = g_debug_flags; g_debug_flags = flags; return old; }
 
 extern "C" int sdb_max_group_len(void) { return SDB_MAX_GROUP_LEN; }
 

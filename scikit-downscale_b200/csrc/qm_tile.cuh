@@ -100,7 +100,8 @@ template <int E, int BATCH, int LDP>
 __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__ src, int64_t ld, int64_t C,
                                           int64_t c0, const int32_t* __restrict__ rg, int n,
                                           const uint8_t* __restrict__ valid, bool allow_vec,
-                                          int32_t* rowtab = nullptr) {
+                                          int32_t* rowtab = nullptr, int tid = -1) {
+    const int tix = tid < 0 ? (int)threadIdx.x : tid;      // thread index inside the 256-thread group that loads this tile
     constexpr int NPS = TileGeom<E>::NPS;
     static_assert(TILE_CT == 8, "the vector path assumes 8-cell tiles");
     // zeros around the group: members -4..-1 and n..NP+4 of every row (the rolling window and the
@@ -110,14 +111,14 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
     if (vec && BATCH != 0) {
         // the vector path below writes every position 0..NP-1 itself (zeros from n on): only the 4 + 5
         // halo slots outside [0, NP) are left
-        if (threadIdx.x < TILE_CT * 9) {
-            const int r = threadIdx.x / 9, k9 = threadIdx.x - r * 9;
+        if (tix < TILE_CT * 9) {
+            const int r = tix / 9, k9 = tix - r * 9;
             tile[r * NPS + skew(k9 < 4 ? k9 - 4 : TileGeom<E>::NP + k9 - 4)] = 0.0f;
         }
     } else {
         const int tail = TileGeom<E>::NP + 5 - n;
         const int per_row = 4 + tail;
-        for (int i = threadIdx.x; i < TILE_CT * per_row; i += TILE_THREADS) {
+        for (int i = tix; i < TILE_CT * per_row; i += TILE_THREADS) {
             const int r = i / per_row, k9 = i - r * per_row;
             tile[r * NPS + skew(k9 < 4 ? k9 - 4 : n + k9 - 4)] = 0.0f;
         }
@@ -126,13 +127,13 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
         // BATCH row segments per thread are loaded before their shared stores (BATCH = 0: leave the
         // scheduling of the unrolled loop to the compiler — fewer live registers)
         constexpr int IT = TileGeom<E>::NP / (TILE_THREADS / 2);
-        const int quad = threadIdx.x & 1;
+        const int quad = tix & 1;
         const int64_t cq = c0 + 4 * quad;
         bool ok0 = true, ok1 = true, ok2 = true, ok3 = true;
         if (valid) { ok0 = valid[cq]; ok1 = valid[cq + 1]; ok2 = valid[cq + 2]; ok3 = valid[cq + 3]; }
         float* d0 = tile + (4 * quad) * NPS;
         const float* col = src + cq;
-        const int j0 = threadIdx.x >> 1;
+        const int j0 = tix >> 1;
         if constexpr (BATCH == 0) {
 #pragma unroll 8
             for (int j = j0; j < n; j += TILE_THREADS / 2) {
@@ -177,13 +178,13 @@ __device__ __forceinline__ void load_tile(float* tile, const float* __restrict__
             }
         }
     } else {
-        const int cc = threadIdx.x & (TILE_CT - 1);
+        const int cc = tix & (TILE_CT - 1);
         const int64_t c = c0 + cc;
         const bool ok = c < C && (!valid || valid[c]);
         float* dst = tile + cc * NPS;
         const float* col = src + (ok ? c : 0);
         constexpr int RS = TILE_THREADS / TILE_CT;       // rows per pass
-        for (int jb = threadIdx.x / TILE_CT; jb < n; jb += 8 * RS) {
+        for (int jb = tix / TILE_CT; jb < n; jb += 8 * RS) {
             int32_t row[8];
             float x[8];
 #pragma unroll

@@ -7,9 +7,11 @@ char* sdb_error_buffer() {
     static thread_local char buf[kErrLen] = {0};
     return buf;
 }
+int g_debug_flags = 0;      // sdb_set_debug_flags: process-wide testing aid (see include/sdb.h)
 }  // namespace sdb
 
-extern "C" int sdb_version(void) { return 100; }   /* 0.1.0 */
+extern "C" int sdb_set_debug_flags(int flags) { int old = sdb::g_debug_flags; sdb::g_debug_flags = flags; return old; }
+extern "C" int sdb_version(void) { return 200; }   /* 0.2.0 */
 extern "C" const char* sdb_last_error(void) { return sdb::sdb_error_buffer(); }
 
 extern "C" int sdb_memcpy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,

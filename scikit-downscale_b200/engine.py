@@ -215,6 +215,60 @@ def qm_fit(y: torch.Tensor, sort_table: GroupTable, *, valid=None, X=None, mean_
     return qm_fit_into(st, y, X, mean_how)
 
 
+FUSED_MAX_LEN = 1024
+
+
+def fused_supported(dtype, table: GroupTable) -> bool:
+    """Whether :func:`qm_fit_predict` covers this case (float32, groups of up to 1024 steps)."""
+    return dtype == torch.float32 and 0 < table.max_len <= FUSED_MAX_LEN
+
+
+def qm_fit_predict(y: torch.Tensor, X_pred: torch.Tensor, table: GroupTable, mode: int, *, X_train=None,
+                   return_anoms: bool = False, valid=None, out=None, keep_state: bool = True, stats=None):
+    """fit + predict in one pass when both share the time index (``sdb_bcsd_fit_predict``): the sorted
+    training values stay in shared memory.  Returns ``(out, fitted state)``; with ``keep_state=False`` the
+    state holds the climatologies only (no sorted values are written).  bcsd.py:115-185, 197-269;
+    quantile.py:81-147."""
+    lib = _lib.load()
+    ld_y = _check_2d(y, 'y')
+    ld_p = _check_2d(X_pred, 'X_pred')
+    T, C = y.shape
+    if X_pred.shape != (T, C):
+        raise ValueError('the fused path needs X_pred shaped like y (same time index)')
+    if y.dtype != torch.float32 or X_pred.dtype != torch.float32:
+        raise TypeError('the fused path is float32 only')
+    if X_train is not None:
+        if X_train.shape != (T, C) or X_train.dtype != y.dtype or _check_2d(X_train, 'X_train') != ld_y:
+            raise ValueError('X_train must be laid out like y')
+    dev = y.device
+    need_x = mode == _lib.MODE_BCSD_T
+    need_y = mode != _lib.MODE_QM
+    if need_x and X_train is None:
+        raise ValueError('BcsdTemperature needs X_train')
+    if keep_state:
+        st = alloc_state(y.dtype, C, dev, table, None, need_x_climo=need_x, need_y_climo=need_y)
+    else:
+        _, length = table.device(dev)
+        st = QMFitted(dtype=y.dtype, n_cells=C, sort_table=table, state_off=np.zeros(0, np.int64), state_ld=0,
+                      sorted_state=None, fit_len_dev=length, state_off_dev=None, mean_table=table,
+                      x_climo=torch.empty((table.n_groups, C), dtype=y.dtype, device=dev) if need_x else None,
+                      y_climo=torch.empty((table.n_groups, C), dtype=y.dtype, device=dev) if need_y else None,
+                      nonfinite=torch.zeros(1, dtype=torch.int32, device=dev))
+    st.valid = valid
+    rows, length = table.device(dev)
+    if out is None:
+        out = torch.empty((T, C), dtype=y.dtype, device=dev)
+    ld_out = _check_2d(out, 'out')
+    _lib.check(lib.sdb_bcsd_fit_predict(mode, _ptr(X_train) if need_x else None, _ptr(y), _ptr(X_pred), _code(y),
+                                        ld_y, ld_p, C, _ptr(rows), _ptr(length), table.n_groups, table.rows.shape[1],
+                                        _ptr(st.x_climo), _ptr(st.y_climo), C, int(bool(return_anoms)),
+                                        _ptr(st.sorted_state) if keep_state else None, st.state_ld,
+                                        _ptr(st.state_off_dev) if keep_state else None,
+                                        _ptr(out), ld_out, _ptr(valid), _ptr(st.nonfinite), _ptr(stats), _stream()),
+               'sdb_bcsd_fit_predict')
+    return out, st
+
+
 def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, return_anoms: bool = False,
                roll_nbr: np.ndarray | None = None, out_dtype=None, want_rank: bool = False, out=None,
                climo_gid: np.ndarray | None = None, cunnane=None):

@@ -100,6 +100,37 @@ class BcsdBase(TimeSynchronousDownscaler):
         self.n_features_in_ = 1
         return self
 
+    def fit_predict_batched(self, X: torch.Tensor, y: torch.Tensor, X_pred: torch.Tensor, index, valid=None, out=None,
+                            keep_state: bool = True, stats=None, fused: bool | None = None):
+        """``fit(X, y)`` followed by ``predict(X_pred)`` on the SAME time index.
+
+        ``fused=True`` runs both in one pass (``sdb_bcsd_fit_predict``, the counting-rank kernel of
+        csrc/qm_fused.cuh): bit-identical to the two calls and without the fitted state's round trip through
+        HBM (dram traffic = the algorithmic bytes), but on B200 it is the SLOWER path (shared-memory bound,
+        one CTA per SM — profiles/README.md, round 2), so the default (``fused=None`` → environment variable
+        ``SDB_FUSED``, off) issues the two calls.  The fused kernel does not cover float64, 'daily_nasa-nex',
+        detrending mappers or groups longer than 1024 steps; those always take the two calls.  The model is
+        fitted afterwards (``keep_state=False`` on the fused path keeps the climatologies only)."""
+        import os
+        self._pre_fit()
+        if fused is None:
+            fused = os.environ.get('SDB_FUSED', '0') not in ('', '0')
+        if fused and self.timestep == 'monthly' and not self._detrend:
+            table = engine.GroupTable(groups_from_keys(grouper_keys(self.time_grouper, index)))
+            if engine.fused_supported(y.dtype, table) and X_pred.dtype == y.dtype and X_pred.shape == y.shape:
+                res, st = engine.qm_fit_predict(y, X_pred, table, self._mode, X_train=X if self._needs_x_climo else None,
+                                                return_anoms=self.return_anoms, valid=valid, out=out,
+                                                keep_state=keep_state, stats=stats)
+                if keep_state:
+                    self._state = st
+                else:
+                    self._climo_state = st
+                    self.__dict__.pop('_state', None)
+                self.n_features_in_ = 1
+                return res
+        self.fit_batched(X, y, index, valid=valid)
+        return self.predict_batched(X_pred, index, out=out)
+
     def check_fit(self):
         """Deferred (synchronising) checks of fit: NaN/inf inputs (base.py:18-20) and the
         precipitation climatology (bcsd.py:140-141)."""
