@@ -51,6 +51,10 @@ def parse():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--debug-flags', type=int, default=None, help='sdb_set_debug_flags value (kernel variant experiments)')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the other BASELINE.json configurations')
+    ap.add_argument('--secondary-seconds', type=float, default=60.0, help='time budget of the secondary list')
+    ap.add_argument('--gather-chunk', type=int, default=16200, help='cells per pushed chunk of the in-path gather')
+    ap.add_argument('--fused', action='store_true', help='also time the fused counting-rank entry (sdb_bcsd_fit_predict)')
     return ap.parse_args()
 
 
@@ -216,12 +220,161 @@ def ncu_limiter(kernel: str):
         return None
 
 
+def gpu_numa_affinity(dev_index: int):
+    """Bind this process (and so its pinned allocations, first touched here) to the CPUs of the NUMA node the GPU
+    hangs off: with eight ranks staging 23 GB per step each through one host, crossing the socket interconnect is
+    what round 1 measured as 0.30 end-to-end scaling efficiency.  Returns (description, previous affinity)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(dev_index)
+        pci = f'{bus.pci_domain_id:04x}:{bus.pci_bus_id:02x}:{bus.pci_device_id:02x}.0'
+        base = f'/sys/bus/pci/devices/{pci}'
+        node = int(open(f'{base}/numa_node').read())
+        cpus = open(f'{base}/local_cpulist').read().strip()
+        ids = set()
+        for part in cpus.split(','):
+            lo, _, hi = part.partition('-')
+            ids.update(range(int(lo), int(hi or lo) + 1))
+        old = os.sched_getaffinity(0)
+        ids &= old
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {'pci': pci, 'numa_node': node, 'cpus': cpus, 'bound': bool(ids)}, old
+    except Exception as ex:      # noqa: BLE001
+        return {'error': repr(ex)[:200]}, None
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
             return float(json.load(f)['hbm_gbs']), 'MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)'
     except Exception:
         return 6650.0, 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------- secondary: BASELINE configs 2-5
+def run_secondary(a, dev, world, rank, barrier, reduce_max, peak):
+    """The other BASELINE.json configurations, measured in the same run after the headline (device-resident
+    inputs, CUDA events, max over ranks; per-GPU cell counts as BASELINE states them, or the largest that fits
+    the time budget — stated per entry).  Under --gpus N every rank runs its own shard (weak scaling)."""
+    import torch
+    import synth
+    from skdownscale_b200.pointwise_models import AnalogRegression, BcsdPrecipitation, PureAnalog, QuantileMapper
+    t_begin = time.perf_counter()
+    out_list = []
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+
+    def left():
+        return a.secondary_seconds - (time.perf_counter() - t_begin)
+
+    def timed(fn, warmup, steps):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return reduce_max(e0.elapsed_time(e1) / steps)
+
+    def entry(name, cells, T, ms, alg_bytes, **extra):
+        cts = world * cells * T / (ms * 1e-3)
+        gbs = alg_bytes * cells * T / (ms * 1e-3) / 1e9
+        e = {'config': name, 'cells_per_gpu': cells, 'timesteps': T, 'ms': ms, 'value': cts, 'unit': UNIT,
+             'algorithmic_bytes_per_cell_timestep': alg_bytes, 'algorithmic_GBps_per_gpu': gbs, 'frac_of_hbm_peak': gbs / peak}
+        e.update(extra)
+        out_list.append(e)
+
+    def guarded(name, fn):
+        try:
+            fn()
+        except Exception as ex:      # noqa: BLE001 - a failed secondary entry must not lose the headline line
+            out_list.append({'config': name, 'error': repr(ex)[:300]})
+        torch.cuda.empty_cache()
+
+    T = 10950
+    idx = synth.daily_index(T)
+
+    def precip(shape, p_dry):
+        g = torch._standard_gamma(torch.full(shape, 0.8, device=dev, dtype=torch.float32)).mul_(6.0)
+        g[torch.rand(shape, device=dev, generator=gen) < p_dry] = 0.0
+        return g
+
+    # -- config 2: QuantileMapper, 10 000 cells x 10 950 days, one 10 950-step group per cell
+    def c2():
+        C = 10000
+        y = torch.randn((T, C), device=dev, generator=gen) * 2 + 14
+        x = torch.randn((T, C), device=dev, generator=gen) * 3 + 15
+        qm = QuantileMapper()
+        ms = timed(lambda: (qm.fit_batched(y), qm.transform_batched(x)), 2, 5)
+        entry('QuantileMapper fit+transform, 10000 cells x 10950 days, one 10950-step group per cell (BASELINE config 2)',
+              C, T, ms, 12, kernels='qm_fit_long_kernel + qm_predict_long_kernel (counting rank)')
+    guarded('QuantileMapper 10000 x 10950', c2)
+
+    # -- config 3 per GPU: BcsdPrecipitation, zero-inflated gamma, the 129 600-cell shard
+    def c3():
+        C = a.cells_per_gpu
+        ytr, xp = precip((T, C), 0.5), precip((T, C), 0.55)
+        bp = BcsdPrecipitation()
+        out = torch.empty((T, C), device=dev)
+        ms = timed(lambda: (bp.fit_batched(ytr, ytr, idx), bp.predict_batched(xp, idx, out=out)), 2, 4)
+        bp.check_fit()
+        entry(f'BcsdPrecipitation fit+predict, zero-inflated gamma, {C} cells x 10950 days (BASELINE config 3, per-GPU shard)', C, T, ms, 12)
+    guarded('BcsdPrecipitation shard', c3)
+
+    # -- config 3 as stated: the whole 720 x 1440 grid on ONE GPU, resident, processed in 8 cell tiles
+    def c3_full():
+        tiles, Ct = 8, 129600
+        C = tiles * Ct
+        free, _ = torch.cuda.mem_get_info(dev)
+        need = 3 * T * C * 4 + 4 * T * Ct * 4
+        if free < need + (4 << 30):
+            raise RuntimeError(f'needs {need / 1e9:.0f} GB of device memory, {free / 1e9:.0f} GB free')
+        ytr = torch.empty((T, C), device=dev)
+        xp = torch.empty((T, C), device=dev)
+        out = torch.empty((T, C), device=dev)
+        for k in range(tiles):
+            ytr[:, k * Ct:(k + 1) * Ct] = precip((T, Ct), 0.5)
+            xp[:, k * Ct:(k + 1) * Ct] = precip((T, Ct), 0.55)
+        bp = BcsdPrecipitation()
+
+        def step():
+            for k in range(tiles):
+                s = slice(k * Ct, (k + 1) * Ct)
+                bp.fit_batched(ytr[:, s], ytr[:, s], idx)
+                bp.predict_batched(xp[:, s], idx, out=out[:, s])
+        ms = timed(step, 1, 2)
+        entry('BcsdPrecipitation fit+predict, zero-inflated gamma, 720x1440 = 1036800 cells x 10950 days on ONE GPU '
+              '(BASELINE config 3: y_train / X_pred / out resident = 136 GB, 8 tiles of 129600 cells, row stride 1036800)', C, T, ms, 12)
+    if world == 1 and left() > 25:
+        guarded('BcsdPrecipitation full grid on one GPU', c3_full)
+
+    # -- configs 4 / 5: analog models, k = 10, 3 predictors; cell count per GPU = BASELINE's, or what the budget allows
+    def analog(name, make, Tn, want_cells, probe_cells=2048):
+        def run(Cn, steps):
+            X = torch.randn((Tn, 3, Cn), device=dev, generator=gen)
+            w = torch.tensor([1.0, 0.5, -0.3], device=dev)[None, :, None]
+            yv = (X * w).sum(1) + 0.3 * torch.randn((Tn, Cn), device=dev, generator=gen)
+            Xq = torch.randn((Tn, 3, Cn), device=dev, generator=gen)
+            m = make()
+            m.fit_batched(X, yv)
+            return timed(lambda: m.predict_batched(Xq), 1, steps)
+        ms_probe = run(probe_cells, 1)
+        budget_ms = max(2.0, min(left() - 8.0, 20.0)) * 1e3 / 2.2          # warm-up + 1 timed step + generation
+        cells = int(min(want_cells, max(probe_cells, budget_ms / ms_probe * probe_cells)) // 1024 * 1024) or probe_cells
+        cells = min(cells, want_cells)
+        ms = run(cells, 1) if cells != probe_cells else ms_probe
+        entry(f'{name}, {cells} cells/GPU x {Tn} days' + ('' if cells == want_cells else f' (BASELINE: {want_cells} cells/GPU; bounded by the bench time budget)'),
+              cells, Tn, ms, 40, distance_evals_per_s=world * cells * float(Tn) * Tn / (ms * 1e-3))
+    if left() > 12:
+        guarded('PureAnalog', lambda: analog('PureAnalog(n_analogs=10, kind=mean_analogs), 3 predictors (BASELINE config 4)',
+                                           lambda: PureAnalog(n_analogs=10, kind='mean_analogs'), 18250, 25000))
+    if left() > 12:
+        guarded('AnalogRegression', lambda: analog('AnalogRegression(n_analogs=10), 3 predictors (BASELINE config 5)',
+                                                 lambda: AnalogRegression(n_analogs=10), 10950, 129600))
+    return out_list
 
 
 def run_b200(a):
@@ -304,35 +457,97 @@ def run_b200(a):
     value = world * C * T / (ms_step * 1e-3)
     model._state.check_finite()
 
-    # ---- the only collective of the path: gather of the predicted field (reported separately)
+    # ---- parity of the field that was just timed: sampled cells against the oracle (numpy port of the reference)
+    parity = None
+    if rank == 0:
+        import oracle
+        cells = [0, C // 2 + 3, C - 1]
+        xs, ys, ps = (t[:, cells].cpu().numpy() for t in (Xtr, ytr, Xp))
+        got = out[:, cells].cpu().numpy().astype(np.float64)
+        groups = oracle.groups_from_keys(oracle.month_keys(idx))
+        worst = 0.0
+        for k in range(len(cells)):
+            st = oracle.bcsd_temperature_fit(xs[:, k], ys[:, k], groups)
+            ref = oracle.bcsd_temperature_predict(st, ps[:, k], groups, groups, True).astype(np.float32).astype(np.float64)
+            worst = max(worst, float(np.max(np.abs(got[:, k] - ref) / np.maximum(np.abs(ref), np.std(ys[:, k])))))
+        parity = {'cells': cells, 'max_err_rel_to_max(|ref|,sigma_y)': worst, 'tolerance': 1e-5, 'ok': bool(worst <= 1e-5)}
+        if not parity['ok']:
+            raise SystemExit(f'bench: the timed field is outside the parity tolerance: {parity}')
+
+    # ---- the fused counting-rank entry on the same inputs (opt-in: measured slower on B200)
+    fused = None
+    if a.fused:
+        out_f = torch.empty_like(out)
+        fm = BcsdTemperature(return_anoms=True)
+        for _ in range(2):
+            fm.fit_predict_batched(Xtr, ytr, Xp, idx, out=out_f, keep_state=False, fused=True)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(a.steps):
+            fm.fit_predict_batched(Xtr, ytr, Xp, idx, out=out_f, keep_state=False, fused=True)
+        f1.record()
+        barrier()
+        fused = {'ms_per_step': f0.elapsed_time(f1) / a.steps, 'bit_identical_to_split': bool(torch.equal(out_f, out)),
+                 'what': 'sdb_bcsd_fit_predict: climatologies + ONE kernel (counting rank in shared memory, no fitted state in HBM)'}
+        del out_f
+
+    # ---- the gather of the predicted field INSIDE the path: every finished cell chunk is pushed by the copy
+    # engines into every peer's replica of the full field while the next chunk is computed (PeerGather)
     gather = None
     if world > 1:
-        from skdownscale_b200.distributed import gather_cells
-        fullf = gather_cells(out, world * C)          # warm-up (NCCL communicator setup)
-        del fullf
+        from skdownscale_b200.distributed import PeerGather
+        pg = PeerGather(T, world * C, torch.float32, dev)
+
+        def gstep():
+            model.fit_batched(Xtr, ytr, idx)
+            return model.predict_gathered(Xp, idx, pg, chunk_cells=a.gather_chunk)
+
+        gstep()                                          # warm-up (peer mappings, streams)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tg0 = time.perf_counter()
         g0.record()
-        fullf = gather_cells(out, world * C)
+        for _ in range(a.steps):
+            fullf = gstep()
         g1.record()
         barrier()
-        gms = torch.tensor([g0.elapsed_time(g1)], device=dev, dtype=torch.float64)
+        wall_g = (time.perf_counter() - tg0) * 1e3
+        gms = torch.tensor([max(g0.elapsed_time(g1), wall_g) / a.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+        # every rank's replica must hold what each peer computed: checksum of every rank's own block ...
+        rows = torch.arange(0, T, 97, device=dev)
+        mine = pg.local.index_select(0, rows).double().sum().reshape(1)
+        sums = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(sums, mine)
+        ok_g = True
+        for r in range(world):                           # ... against the same block of MY replica
+            blk = fullf[:, r * C:(r + 1) * C].index_select(0, rows).double().sum()
+            ok_g = ok_g and bool(blk == sums[r][0])
+        ok_t = torch.tensor([1 if ok_g and torch.equal(pg.local, out) else 0], device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
         recv = (world - 1) * T * C * 4
-        gather = {'ms': float(gms.item()), 'bytes_received_per_gpu': recv,
-                  'GB/s_per_gpu': recv / (float(gms.item()) * 1e-3) / 1e9,
-                  'what': 'NCCL all-gather of the predicted field [T, cells] + local re-interleave to cell-fastest layout'}
-        del fullf
+        step_g = float(gms.item())
+        gather = {'ms_per_step_with_gather': step_g, 'value_with_gather': world * C * T / (step_g * 1e-3),
+                  'bytes_received_per_gpu': recv, 'GB/s_per_gpu_over_the_step': recv / (step_g * 1e-3) / 1e9,
+                  'field_verified_on_every_rank': bool(ok_t.item()),
+                  'floor_ms': recv / 770e9 * 1e3,
+                  'what': 'fit + predict in %d-cell chunks written straight into the rank\'s columns of a full [T, n_cells] replica; '
+                          'finished chunks pushed to all peers with cudaMemcpy2DAsync on IPC-mapped peer memory (copy engines, one stream '
+                          'per peer) while the next chunk computes; floor_ms = bytes received / 770 GB/s measured peer-copy bandwidth'
+                          % a.gather_chunk}
+        del fullf, pg
         torch.cuda.empty_cache()
 
     # ---- end to end through the public API: pinned host inputs, H2D + fit + predict + D2H per step
     e2e = None
     if not a.no_e2e:
+        numa, old_affinity = gpu_numa_affinity(local)
         h = [torch.empty((T, C), dtype=torch.float32, pin_memory=True) for _ in range(4)]
         for dst, src in zip(h[:3], (Xtr, ytr, Xp)):
             dst.copy_(src)
         torch.cuda.synchronize()
-        del Xtr, ytr, Xp, out
+        Xtr = ytr = Xp = out = None
         model._state = None
         torch.cuda.empty_cache()
         pw = PointWiseDownscaler(BcsdTemperature(return_anoms=True), device=dev)
@@ -355,9 +570,29 @@ def run_b200(a):
         tms = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e2e = {'value': world * C * T * a.e2e_steps / (float(tms.item()) * 1e-3), 'unit': UNIT,
+        step_s = float(tms.item()) * 1e-3 / a.e2e_steps
+        e2e = {'value': world * C * T / step_s, 'unit': UNIT,
                'h2d_bytes_per_step': 3 * T * C * 4, 'd2h_bytes_per_step': T * C * 4, 'steps': a.e2e_steps,
+               'h2d_GBps_per_rank': 3 * T * C * 4 / step_s / 1e9, 'd2h_GBps_per_rank': T * C * 4 / step_s / 1e9,
+               'host_binding_rank0': numa,
                'path': 'PointWiseDownscaler.fit(X, y) + .predict(X, out=pinned) on pinned host tensors: 16384-cell chunks, H2D / kernels / D2H overlapped on three streams'}
+
+        h = pw = None
+        if old_affinity:
+            os.sched_setaffinity(0, old_affinity)        # the CPU baseline below uses every core again
+
+    secondary = None
+    if not a.no_secondary:
+        Xtr = ytr = Xp = out = None                      # (already released when the e2e section ran)
+        model._state = None
+        torch.cuda.empty_cache()
+
+        def reduce_max(v):
+            t = torch.tensor([v], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        secondary = run_secondary(a, dev, world, rank, barrier, reduce_max, measured_peak()[0])
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -375,6 +610,9 @@ def run_b200(a):
             'clocks': clocks,
             'e2e': e2e,
             'gather': gather,
+            'value_with_gather': gather['value_with_gather'] if gather else None,
+            'parity_check': parity,
+            'fused_counting_rank': fused,
             'gpu_launches': 4 * a.steps,
             'roofline': {'bound': 'hbm', 'kernel': 'qm_predict_tile_kernel<32,true> (dominant)', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                          'frac': ach / peak, 'traffic': ncu_traffic('qm_predict_tile_kernel<32,true>', float(C) * T),
@@ -386,8 +624,9 @@ def run_b200(a):
                          'whole_step': {'achieved': ach_step, 'frac': ach_step / peak,
                                         'algorithmic_bytes_per_cell_timestep': ALG_BYTES_STEP}},
         }
-        if world == 1 and not a.no_cpu:
+        if not a.no_cpu:
             line['cpu_baseline'] = cpu_baseline(T, a.cpu_seconds)
+        line['secondary'] = secondary
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

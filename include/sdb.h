@@ -98,9 +98,13 @@ const char* sdb_last_error(void);
  * thread-safety paragraph above): set it before issuing work, not concurrently with it. */
 int sdb_set_debug_flags(int flags);
 
-/* Strided host<->device copy of a [height, width_bytes] block (cudaMemcpy2DAsync) on `stream`:
- * how a column block (cell range) of a time-major host array travels to / from the device.
- * kind: 0 = host to device, 1 = device to host.  Pitches in bytes. */
+/* Strided copy of a [height, width_bytes] block (cudaMemcpy2DAsync) on `stream`: how a column block (cell
+ * range) of a time-major array travels host <-> device (kind 0 = host to device, 1 = device to host) and, with
+ * kind 2 (cudaMemcpyDefault), device <-> device INCLUDING a peer GPU's memory mapped into this process (CUDA
+ * IPC): the gather of the predicted field — every rank's out[T, C_rank] block is pushed by the copy engines
+ * into columns [c0, c0 + C_rank) of each peer's full [T, n_cells] field over NVLink while the next cell
+ * chunk is still being computed (north_star's "final gather of the predicted field"; the reference has no
+ * equivalent, its dask workers return blocks to the client, core.py:262,336).  Pitches in bytes. */
 int sdb_memcpy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
                        int64_t width_bytes, int64_t height, int kind, void* stream);
 

@@ -96,6 +96,7 @@ extern "C" int sdb_qm_fit(const void* y, int dtype, int64_t ld, int64_t n_cells,
     if (dtype == SDB_F32 && !(g_debug_flags & 1)) {
         if (max_len <= 256) return qm_fit_tile_np256(f, st);
         if (max_len <= 1024) return qm_fit_tile_np1024(f, st);
+        if (max_len <= SDB_MAX_GROUP_LEN) return qm_fit_long(f, st);
     }
     switch (pick_np(max_len)) {
         case 256:   return qm_fit_np256(dtype, f, st);
@@ -151,6 +152,8 @@ extern "C" int sdb_qm_predict(int mode, const void* X, int dtype, int64_t ld, in
         if (longest <= 256) return qm_predict_tile_np256(kind, p, st);
         return qm_predict_tile_np1024(kind, p, st);
     }
+    if (dtype == SDB_F32 && kind == KIND_RAW && max_len > 1024 && max_len <= SDB_MAX_GROUP_LEN && !(g_debug_flags & 1))
+        return qm_predict_long(p, st);
     switch (pick_np(max_len)) {
         case 256:   return qm_predict_np256(dtype, kind, p, st);
         case 1024:  return qm_predict_np1024(dtype, kind, p, st);

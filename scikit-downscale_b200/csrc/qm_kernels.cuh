@@ -367,6 +367,10 @@ int qm_fit_tile_np1024(const FitParams& f, cudaStream_t st);
 int qm_predict_tile_np256(int kind, const PredictParams& p, cudaStream_t st);
 int qm_predict_tile_np1024(int kind, const PredictParams& p, cudaStream_t st);
 
+// long float32 groups by counting rank (qm_long.cu)
+int qm_fit_long(const FitParams& f, cudaStream_t st);
+int qm_predict_long(const PredictParams& p, cudaStream_t st);
+
 // per-size entry points, defined in qm_np<N>.cu
 #define SDB_DECLARE_SIZE(NP)                                                             \
     int qm_fit_np##NP(int dtype, const FitParams& f, cudaStream_t st);                   \

@@ -54,3 +54,75 @@ def gather_cells(local: torch.Tensor, n_cells: int, group=None, stacked: bool = 
     if all(b - a == wmax for a, b in spans):
         return full.movedim(0, -2).reshape(lead + (world * wmax,))     # [.., world, C_rank] → cells contiguous
     return torch.cat([full[r][..., : (b - a)] for r, (a, b) in enumerate(spans)], dim=-1)
+
+
+class PeerGather:
+    """The gather of the predicted field INSIDE the path: every rank owns a full ``[T, (k,) n_cells]`` replica,
+    predicts straight into its own column block of it (``ld_out = n_cells``, no staging buffer) and pushes
+    finished cell chunks into the same columns of every peer's replica with the copy engines
+    (``cudaMemcpy2DAsync`` on peer memory mapped through CUDA IPC, one stream per peer) while the next chunk is
+    still being computed.  No re-interleave, no second full-size buffer, no SM time.
+
+    Usage (one process per GPU, default process group initialised)::
+
+        g = PeerGather(T, n_cells, torch.float32, device)
+        for c0, c1 in g.chunks(16200):                 # local cell numbers of this rank's shard
+            model.predict_cells(c0, c1, out=g.local[:, c0:c1])
+            g.push(c0, c1)
+        field = g.finish()                               # [T, n_cells] complete on every rank
+    """
+
+    def __init__(self, n_steps: int, n_cells: int, dtype, device, n_outputs: int | None = None, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device(device)
+        shape = (n_steps, n_cells) if n_outputs is None else (n_steps, n_outputs, n_cells)
+        self.full = torch.empty(shape, dtype=dtype, device=self.device)
+        self.a, self.b = cell_range(n_cells, self.world, self.rank)
+        self.local = self.full[..., self.a:self.b]
+        self.peers = [None] * self.world
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, reduce_tensor(self.full), group=group)
+            for r, (rebuild, args) in enumerate(handles):
+                if r != self.rank:
+                    self.peers[r] = rebuild(*args)           # the peer's replica, mapped into this process
+            with torch.cuda.device(self.device):
+                self.streams = [torch.cuda.Stream(self.device) if r != self.rank else None for r in range(self.world)]
+        self.bytes_pushed = 0
+
+    def chunks(self, chunk_cells: int):
+        w = self.b - self.a
+        return [(c0, min(c0 + chunk_cells, w)) for c0 in range(0, w, chunk_cells)]
+
+    def push(self, c0: int, c1: int) -> None:
+        """Send local cells [c0, c1) (already written into ``self.local`` on the current stream) to every peer."""
+        if self.world == 1:
+            return
+        from . import engine
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        lead = self.full.shape[:-1]
+        rows = int(torch.tensor(lead).prod().item()) if len(lead) > 1 else lead[0]
+        src = self.full.view(rows, self.full.shape[-1])[:, self.a + c0:self.a + c1]
+        with torch.cuda.device(self.device):
+            # start with the next rank so that at any moment the eight senders aim at eight different receivers
+            for k in range(1, self.world):
+                r = (self.rank + k) % self.world
+                st = self.streams[r]
+                st.wait_event(ready)
+                dst = self.peers[r].view(rows, self.full.shape[-1])[:, self.a + c0:self.a + c1]
+                engine.copy2d(dst, src, 'peer', stream=st.cuda_stream)
+                self.bytes_pushed += src.numel() * src.element_size()
+
+    def finish(self) -> torch.Tensor:
+        """Wait for this rank's pushes, then for everybody's: the replica is complete."""
+        if self.world > 1:
+            for st in self.streams:
+                if st is not None:
+                    st.synchronize()
+            torch.cuda.current_stream(self.device).synchronize()
+            dist.barrier(group=self.group)
+        return self.full

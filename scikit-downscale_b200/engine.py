@@ -142,9 +142,10 @@ def group_mean(v: torch.Tensor, table: GroupTable, how: int, valid=None, nonfini
     return out
 
 
-def copy2d(dst: torch.Tensor, src: torch.Tensor, to_device: bool, stream=None) -> None:
+def copy2d(dst: torch.Tensor, src: torch.Tensor, to_device, stream=None) -> None:
     """Asynchronous strided copy of a [rows, cols] block between host and device (both tensors may
-    be column slices of wider arrays) — cudaMemcpy2DAsync through the C ABI."""
+    be column slices of wider arrays) — cudaMemcpy2DAsync through the C ABI.  ``to_device``: True = host →
+    device, False = device → host, ``'peer'`` = device → device (possibly another GPU's memory mapped by IPC)."""
     lib = _lib.load()
     if dst.shape != src.shape or dst.dim() != 2 or dst.dtype != src.dtype:
         raise ValueError('copy2d needs two [rows, cols] tensors of the same shape and dtype')
@@ -154,7 +155,7 @@ def copy2d(dst: torch.Tensor, src: torch.Tensor, to_device: bool, stream=None) -
     rows, cols = dst.shape
     dp = (dst.stride(0) if rows > 1 else cols) * es
     sp = (src.stride(0) if rows > 1 else cols) * es
-    _lib.check(lib.sdb_memcpy2d_async(_ptr(dst), dp, _ptr(src), sp, cols * es, rows, 0 if to_device else 1,
+    _lib.check(lib.sdb_memcpy2d_async(_ptr(dst), dp, _ptr(src), sp, cols * es, rows, 2 if to_device == 'peer' else (0 if to_device else 1),
                                       stream if stream is not None else _stream()), 'sdb_memcpy2d_async')
 
 

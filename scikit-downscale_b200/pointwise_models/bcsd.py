@@ -159,6 +159,24 @@ class BcsdBase(TimeSynchronousDownscaler):
                                  roll_nbr=nbr, out_dtype=out_dtype, want_rank=want_rank, out=out,
                                  cunnane=self._cunnane())
 
+    def predict_gathered(self, X: torch.Tensor, index, gather, chunk_cells: int = 16200):
+        """predict this rank's shard in cell chunks straight into its column block of ``gather.full``
+        (:class:`skdownscale_b200.distributed.PeerGather`) and push every finished chunk to the peers while the
+        next one is computed.  Returns the complete ``[T, n_cells]`` field (valid on every rank)."""
+        if not hasattr(self, '_state'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet.")
+        if getattr(self, '_detrend', False):
+            raise NotImplementedError('predict_gathered does not cover qm_kwargs detrend=True')
+        if self.timestep == 'daily' and self.return_anoms:
+            raise ValueError('shape of climo is not equal to input array')
+        table, nbr = self._predict_tables(index)
+        st = self._state
+        for c0, c1 in gather.chunks(chunk_cells):
+            engine.qm_predict(st.cells(c0, c1), X[:, c0:c1], table, self._mode, return_anoms=self.return_anoms,
+                              roll_nbr=nbr, out=gather.local[:, c0:c1], cunnane=self._cunnane())
+            gather.push(c0, c1)
+        return gather.finish()
+
     # ------------------------------------------------------------------ host arrays: chunked H2D → kernels → D2H
     @staticmethod
     def _host2d(a, name):
