@@ -536,7 +536,8 @@ def run_b200(a):
                           'finished chunks pushed to all peers with cudaMemcpy2DAsync on IPC-mapped peer memory (copy engines, one stream '
                           'per peer) while the next chunk computes; floor_ms = bytes received / 770 GB/s measured peer-copy bandwidth'
                           % a.gather_chunk}
-        del fullf, pg
+        del fullf
+        pg.close()
         torch.cuda.empty_cache()
 
     # ---- end to end through the public API: pinned host inputs, H2D + fit + predict + D2H per step

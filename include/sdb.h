@@ -108,6 +108,28 @@ int sdb_set_debug_flags(int flags);
 int sdb_memcpy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
                        int64_t width_bytes, int64_t height, int kind, void* stream);
 
+/* The same copy for device -> device (peer) blocks whose rows are 16-byte aligned multiples of 16 bytes, done by
+ * n_ctas CTAs (<= 0: 32) of plain 16-byte loads / stores instead of the copy engines: the NVLink fast path for
+ * the strided destination of the gather (a column block of the peer's full field).  SDB_E_UNSUPPORTED when the
+ * geometry is not 16-byte aligned (fall back to sdb_memcpy2d_async kind 2). */
+int sdb_peer_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                    int64_t width_bytes, int64_t height, int n_ctas, void* stream);
+
+/* Enable direct (NVLink) access from `device` to memory of `peer_device` for kernels and copies issued on
+ * `device` — required before sdb_peer_copy2d / sdb_memcpy2d_async(kind 2) touch IPC-mapped peer memory (without
+ * it the kernel faults and the copy is staged through the host).  Idempotent. */
+int sdb_enable_peer_access(int device, int peer_device);
+
+/* Peer-visible device buffers for the gather (CUDA IPC).  sdb_peer_alloc: cudaMalloc on the current device +
+ * its 64-byte IPC handle (to be sent to the other ranks by any means); sdb_peer_open: map a peer rank's buffer
+ * into this process for access FROM THE CURRENT DEVICE (lazy peer access over NVLink); close / free undo them.
+ * These are the only entry points that allocate: a framework's caching allocator cannot export IPC handles
+ * for interior pointers. */
+int sdb_peer_alloc(int64_t bytes, void** ptr, void* handle64);
+int sdb_peer_open(const void* handle64, void** ptr);
+int sdb_peer_close(void* ptr);
+int sdb_peer_free(void* ptr);
+
 /* Largest group length supported by sdb_qm_fit / sdb_qm_predict. */
 int sdb_max_group_len(void);
 

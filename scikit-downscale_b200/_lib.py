@@ -35,6 +35,12 @@ SIGNATURES = {
     'sdb_max_group_len': (c_int, []),
     'sdb_set_debug_flags': (c_int, [c_int]),
     'sdb_memcpy2d_async': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    'sdb_enable_peer_access': (c_int, [c_int, c_int]),
+    'sdb_peer_alloc': (c_int, [c_int64, c_void_p, c_void_p]),
+    'sdb_peer_open': (c_int, [c_void_p, c_void_p]),
+    'sdb_peer_close': (c_int, [c_void_p]),
+    'sdb_peer_free': (c_int, [c_void_p]),
+    'sdb_peer_copy2d': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     'sdb_group_mean': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
                                c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'sdb_qm_fit': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -59,9 +59,13 @@ def gather_cells(local: torch.Tensor, n_cells: int, group=None, stacked: bool = 
 class PeerGather:
     """The gather of the predicted field INSIDE the path: every rank owns a full ``[T, (k,) n_cells]`` replica,
     predicts straight into its own column block of it (``ld_out = n_cells``, no staging buffer) and pushes
-    finished cell chunks into the same columns of every peer's replica with the copy engines
-    (``cudaMemcpy2DAsync`` on peer memory mapped through CUDA IPC, one stream per peer) while the next chunk is
-    still being computed.  No re-interleave, no second full-size buffer, no SM time.
+    finished cell chunks into the same columns of every peer's replica (peer memory mapped through CUDA IPC, one
+    stream per peer) while the next chunk is still being computed.  ``method='ce'``: pitched ``cudaMemcpy2DAsync``
+    on the copy engines, no SM time — 557 GB/s per direction measured between two B200s for the 129 600-cell block
+    (profiles/r02_peer_copy_bench.json); ``method='kernel'``: ``sdb_peer_copy2d``, 16-byte loads / stores by
+    ``n_ctas`` CTAs (637 GB/s with 148 CTAs, 686 GB/s with 296).  No re-interleave, no second full-size buffer.
+    The replica is allocated by the library (``sdb_peer_alloc``: an IPC handle names a whole cudaMalloc
+    allocation) and wrapped as a torch tensor without a copy.
 
     Usage (one process per GPU, default process group initialised)::
 
@@ -72,26 +76,69 @@ class PeerGather:
         field = g.finish()                               # [T, n_cells] complete on every rank
     """
 
-    def __init__(self, n_steps: int, n_cells: int, dtype, device, n_outputs: int | None = None, group=None):
-        from torch.multiprocessing.reductions import reduce_tensor
+    def __init__(self, n_steps: int, n_cells: int, dtype, device, n_outputs: int | None = None, group=None,
+                 method: str = 'ce', n_ctas: int = 148):
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        self._lib, self._libmod = lib, _lib
         self.group = group
+        self.method, self.n_ctas = method, n_ctas
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.device = torch.device(device)
-        shape = (n_steps, n_cells) if n_outputs is None else (n_steps, n_outputs, n_cells)
-        self.full = torch.empty(shape, dtype=dtype, device=self.device)
-        self.a, self.b = cell_range(n_cells, self.world, self.rank)
-        self.local = self.full[..., self.a:self.b]
-        self.peers = [None] * self.world
-        if self.world > 1:
-            handles = [None] * self.world
-            dist.all_gather_object(handles, reduce_tensor(self.full), group=group)
-            for r, (rebuild, args) in enumerate(handles):
-                if r != self.rank:
-                    self.peers[r] = rebuild(*args)           # the peer's replica, mapped into this process
-            with torch.cuda.device(self.device):
+        self.shape = (n_steps, n_cells) if n_outputs is None else (n_steps, n_outputs, n_cells)
+        self.dtype = dtype
+        nbytes = int(torch.tensor(self.shape).prod().item()) * torch.empty((), dtype=dtype).element_size()
+        self._own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            _lib.check(lib.sdb_peer_alloc(nbytes, ctypes.byref(self._own), handle), 'sdb_peer_alloc')
+            self.full = self._wrap(self._own.value)
+            self.a, self.b = cell_range(n_cells, self.world, self.rank)
+            self.local = self.full[..., self.a:self.b]
+            self.peers = [None] * self.world
+            self._opened = []
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, (self.device.index, handle.raw), group=group)
+                for r, (peer_dev, h) in enumerate(handles):
+                    if r == self.rank:
+                        continue
+                    p = ctypes.c_void_p()
+                    _lib.check(lib.sdb_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), 'sdb_peer_open')
+                    self._opened.append(p)
+                    self.peers[r] = self._wrap(p.value)      # the peer's replica, mapped for access from THIS device
                 self.streams = [torch.cuda.Stream(self.device) if r != self.rank else None for r in range(self.world)]
         self.bytes_pushed = 0
+
+    def _wrap(self, ptr: int) -> torch.Tensor:
+        """A torch view of raw device memory (zero copy, through ``__cuda_array_interface__``)."""
+        typestr = {torch.float32: '<f4', torch.float64: '<f8'}[self.dtype]
+
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {'shape': tuple(self.shape), 'typestr': typestr, 'data': (ptr, False), 'version': 2}
+        return torch.as_tensor(raw, device=self.device)
+
+    def close(self) -> None:
+        """Unmap the peers' replicas and free the own one (after a barrier: nobody may still be pushing into it)."""
+        if getattr(self, '_own', None) is None:
+            return
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.full = self.local = None
+        self.peers = []
+        with torch.cuda.device(self.device):
+            for p in self._opened:
+                self._libmod.check(self._lib.sdb_peer_close(p), 'sdb_peer_close')
+            self._opened = []
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            self._libmod.check(self._lib.sdb_peer_free(self._own), 'sdb_peer_free')
+        self._own = None
 
     def chunks(self, chunk_cells: int):
         w = self.b - self.a
@@ -114,7 +161,7 @@ class PeerGather:
                 st = self.streams[r]
                 st.wait_event(ready)
                 dst = self.peers[r].view(rows, self.full.shape[-1])[:, self.a + c0:self.a + c1]
-                engine.copy2d(dst, src, 'peer', stream=st.cuda_stream)
+                engine.peer_copy2d(dst, src, stream=st.cuda_stream, n_ctas=self.n_ctas, method=self.method)
                 self.bytes_pushed += src.numel() * src.element_size()
 
     def finish(self) -> torch.Tensor:

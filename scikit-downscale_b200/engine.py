@@ -159,6 +159,24 @@ def copy2d(dst: torch.Tensor, src: torch.Tensor, to_device, stream=None) -> None
                                       stream if stream is not None else _stream()), 'sdb_memcpy2d_async')
 
 
+def peer_copy2d(dst: torch.Tensor, src: torch.Tensor, stream=None, n_ctas: int = 32, method: str = 'kernel') -> None:
+    """Push a [rows, cols] block into (possibly peer) device memory: ``method='kernel'`` = ``sdb_peer_copy2d``
+    (SM loads / stores over NVLink; needs 16-byte aligned rows, else falls back), ``'ce'`` = ``cudaMemcpy2DAsync``."""
+    lib = _lib.load()
+    if dst.shape != src.shape or dst.dim() != 2 or dst.dtype != src.dtype:
+        raise ValueError('peer_copy2d needs two [rows, cols] tensors of the same shape and dtype')
+    es = dst.element_size()
+    rows, cols = dst.shape
+    dp = (dst.stride(0) if rows > 1 else cols) * es
+    sp = (src.stride(0) if rows > 1 else cols) * es
+    st = stream if stream is not None else _stream()
+    aligned = not ((cols * es | dp | sp | dst.data_ptr() | src.data_ptr()) & 15)
+    if method == 'kernel' and aligned:
+        _lib.check(lib.sdb_peer_copy2d(_ptr(dst), dp, _ptr(src), sp, cols * es, rows, n_ctas, st), 'sdb_peer_copy2d')
+    else:
+        _lib.check(lib.sdb_memcpy2d_async(_ptr(dst), dp, _ptr(src), sp, cols * es, rows, 2, st), 'sdb_memcpy2d_async')
+
+
 def alloc_state(dtype, n_cells: int, device, sort_table: GroupTable, mean_table: GroupTable | None = None,
                 need_x_climo: bool = False, need_y_climo: bool = True, with_valid: bool = False) -> QMFitted:
     """Device storage of the fitted state of ``n_cells`` cells (filled by :func:`qm_fit_into`)."""

@@ -52,6 +52,9 @@ def _worker(rank, world, port, q):
         field2 = m.predict_gathered(Xp[:, a:b], idx, g, chunk_cells=64)
         if ok and not torch.equal(field2, ref):
             ok, why = False, 'second predict_gathered differs'
+        ref = ref.clone()
+        field = field2 = None
+        g.close()
         got = D.gather_cells(m.predict_batched(Xp[:, a:b], idx), C)
         if ok and not torch.equal(got, ref):
             ok, why = False, 'NCCL gather_cells differs'
