@@ -245,6 +245,31 @@ int sdb_analog_predict(int kind, const void* X_train, const void* y_train, const
                        const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
 
 /*
+ * The same search with exact pruning (float32 inputs): order_train [t_fit, ld_order] / order_query [t_query,
+ * ld_order] list, per cell, the training rows / query steps in ascending order of the FIRST predictor
+ * (sdb_series_argsort on X_train[:, 0, :] and X_query[:, 0, :] with row_stride = n_features * ld).  A CTA's 256
+ * consecutive queries of that order then only visit the training chunks whose first-predictor gap can still beat
+ * their current k-th distance.  Identical results (neighbours, order, outputs) — the reference prunes the same
+ * search with sklearn's KDTree, gard.py:82,194,299.
+ */
+int sdb_analog_predict_pruned(int kind, const void* X_train, const void* y_train, const void* X_query,
+                              int dtype, int64_t ld, int64_t n_cells,
+                              int t_fit, int t_query, int n_features, int k,
+                              int has_thresh, double thresh, double logistic_c, const int32_t* rand_idx,
+                              void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
+                              const uint8_t* cell_valid, int32_t* nonfinite,
+                              const int32_t* order_train, const int32_t* order_query, int64_t ld_order, void* stream);
+
+/*
+ * order[r * ld_order + c] = index t of the r-th smallest x[t * row_stride + c], t = 0 .. n_steps - 1, for every cell
+ * (equal values in index order; float32; n_steps <= sdb_series_argsort_max_steps() = 32768).  One CTA per cell,
+ * block-wide counting rank (csrc/qm_long.cu).
+ */
+int sdb_series_argsort(const void* x, int dtype, int64_t row_stride, int64_t n_cells, int n_steps,
+                       int32_t* order, int64_t ld_order, const uint8_t* cell_valid, void* stream);
+int sdb_series_argsort_max_steps(void);
+
+/*
  * 1-based rank of every value among its (cell, group) series: the tie-max rank of the quantile map
  * (ordinal = 0; ties share the highest rank, quantile.py:138,488) or the position in (value, time
  * index) order (ordinal = 1; what `np.argsort` yields on tie-free data, quantile.py:239,607).

@@ -66,6 +66,15 @@ SIGNATURES = {
                                    c_int, c_double, c_double, c_void_p,
                                    c_void_p, c_int, c_int64, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
+    'sdb_analog_predict_pruned': (c_int, [c_int, c_void_p, c_void_p, c_void_p,
+                                          c_int, c_int64, c_int64,
+                                          c_int, c_int, c_int, c_int,
+                                          c_int, c_double, c_double, c_void_p,
+                                          c_void_p, c_int, c_int64, c_void_p,
+                                          c_void_p, c_void_p,
+                                          c_void_p, c_void_p, c_int64, c_void_p]),
+    'sdb_series_argsort': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    'sdb_series_argsort_max_steps': (c_int, []),
     'sdb_series_rank': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'sdb_qmr_frame': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int,

@@ -21,53 +21,65 @@
 
 namespace sdb {
 
-constexpr int LG_NT = 512;
+constexpr int LG_NT = 512;                     // threads per CTA of the quantile-mapping kernels (n <= 16 384)
+constexpr int LG_NT_BIG = 1024;                // ... of the argsort kernel (n <= 32 768: the 50-year analog windows)
 constexpr int LG_EPT = 18;                     // entries per thread: stride 36 words keeps 16-byte accesses conflict-free
-constexpr int LG_ENT = LG_NT * LG_EPT;         // 9 216 entries = 294 912 buckets (72 KB)
-constexpr int LG_NB = LG_ENT * 32;
-constexpr int LG_E = 32;                       // elements per thread (n <= 16 384), member j = tid + k * 512
-constexpr int LG_NMAX = LG_NT * LG_E;
-constexpr int LG_W_WORDS = 2 * (LG_ENT + 32);  // + one dummy entry per lane
+constexpr int LG_E = 32;                       // elements per thread, member j = tid + k * NT
+template <int NT> struct LgCfg {
+    static constexpr int ENT = NT * LG_EPT;    // 512 threads: 9 216 entries = 294 912 buckets (72 KB)
+    static constexpr int NB = ENT * 32;
+    static constexpr int NMAX = NT * LG_E;
+    static constexpr int W_WORDS = 2 * (ENT + 32);   // + one dummy entry per lane
+    static constexpr int NWARP = NT / 32;
+};
+constexpr int LG_ENT = LgCfg<LG_NT>::ENT;
+constexpr int LG_NB = LgCfg<LG_NT>::NB;
+constexpr int LG_NMAX = LgCfg<LG_NT>::NMAX;
+constexpr int LG_W_WORDS = LgCfg<LG_NT>::W_WORDS;
 constexpr int LG_SMALL = 8;                    // members of a dirty entry ordered in registers
 constexpr int LG_DECAP = 2048;                 // list of dirty entries (uint16 entry numbers); more: every thread walks its own entries
 
 struct LgShared {
-    float red_lo[16], red_hi[16];
-    uint32_t warp_tot[16];
+    float red_lo[32], red_hi[32];
+    uint32_t warp_tot[32];
     uint32_t n_dirty;
+    uint32_t n_lo_cursor;
     uint16_t de[LG_DECAP];
 };
 
+template <int NT>
 __device__ __forceinline__ void lg_block_minmax(float& lo, float& hi, LgShared* sh) {
     bm_warp_minmax(lo, hi);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (lane == 0) { sh->red_lo[warp] = lo; sh->red_hi[warp] = hi; }
     __syncthreads();
-    lo = sh->red_lo[lane & 15]; hi = sh->red_hi[lane & 15];
+    lo = sh->red_lo[lane % LgCfg<NT>::NWARP]; hi = sh->red_hi[lane % LgCfg<NT>::NWARP];
     bm_warp_minmax(lo, hi);
 }
 
 // phases A + B for the block: v[k] = key of member tid + k * 512 (k < LG_E), `n` members.  Returns the number of
 // inserted elements (keys above the lower bound); afterwards W holds the prefixes.
+template <int NT>
 __device__ __forceinline__ int lg_build(const float (&v)[LG_E], int n, float lo, float scale, uint32_t* W, LgShared* sh) {
+    using G = LgCfg<NT>;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t Wsa = bm_saddr(W);
     {
         uint4* p = reinterpret_cast<uint4*>(W);
-        for (int i = tid; i < LG_W_WORDS / 4; i += LG_NT) p[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (tid == 0) sh->n_dirty = 0u;
+        for (int i = tid; i < G::W_WORDS / 4; i += NT) p[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (tid == 0) { sh->n_dirty = 0u; sh->n_lo_cursor = 0u; }
     }
     __syncthreads();
-    const uint32_t dummy = (uint32_t)(LG_ENT + lane) * 8u;
+    const uint32_t dummy = (uint32_t)(G::ENT + lane) * 8u;
 #pragma unroll
     for (int b = 0; b < LG_E; b += 8) {
-        if (b * LG_NT < n) {                         // CTA-uniform: batches past the end of the group are skipped
+        if (b * NT < n) {                         // CTA-uniform: batches past the end of the group are skipped
             uint32_t q[8];
             int on[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                q[u] = bm_bucket_f32<LG_NB>(v[b + u], lo, scale);
-                on[u] = (v[b + u] > lo) ? n - (tid + (b + u) * LG_NT) : 0;
+                q[u] = bm_bucket_f32<G::NB>(v[b + u], lo, scale);
+                on[u] = (v[b + u] > lo) ? n - (tid + (b + u) * NT) : 0;
             }
             bm_insert_batch<8>(Wsa, dummy, q, on);
         }
@@ -88,13 +100,13 @@ __device__ __forceinline__ int lg_build(const float (&v)[LG_E], int n, float lo,
     }
     if (lane == 31) sh->warp_tot[warp] = incl;
     __syncthreads();
-    uint32_t wt = (lane < 16) ? sh->warp_tot[lane] : 0u, winc = wt;
+    uint32_t wt = (lane < G::NWARP) ? sh->warp_tot[lane] : 0u, winc = wt;
 #pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
+    for (int o = 1; o < G::NWARP; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
         if (lane >= o) winc += t;
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, winc, 15);
+    const uint32_t total = __shfl_sync(0xffffffffu, winc, G::NWARP - 1);
     const uint32_t wbase = __shfl_sync(0xffffffffu, winc - wt, warp);
     uint32_t p = wbase + incl - run;
 #pragma unroll
@@ -119,18 +131,18 @@ __device__ __forceinline__ int lg_build(const float (&v)[LG_E], int n, float lo,
 // [start, start + c) in arrival order.  c <= 8: the owning thread orders them in registers.  Larger entries are
 // handled by the whole warp, one after the other: if all members are EQUAL (the usual way to get there: many
 // exact ties — values on a coarse grid) nothing has to be ordered; otherwise the slow exact path runs.
-template <class Small, class Big>
+template <int NT, class Small, class Big>
 __device__ __forceinline__ void lg_for_dirty_entries(const uint32_t* W, const LgShared* sh, Small&& small, Big&& big) {
     const int tid = threadIdx.x;
     const int nd = (int)sh->n_dirty;
     // one thread per LISTED dirty entry (dense: a few hundred entries = one pass); if the list overflowed,
     // every thread walks the 18 entries it owns instead
     const bool listed = nd <= LG_DECAP;
-    const int trips = listed ? (nd + LG_NT - 1) / LG_NT : LG_EPT;
+    const int trips = listed ? (nd + NT - 1) / NT : LG_EPT;
 #pragma unroll 1
     for (int i = 0; i < trips; ++i) {
         int e = -1;
-        if (listed) { const int k = i * LG_NT + tid; if (k < nd) e = (int)sh->de[k]; }
+        if (listed) { const int k = i * NT + tid; if (k < nd) e = (int)sh->de[k]; }
         else e = tid * LG_EPT + i;
         const uint32_t meta = (e >= 0) ? W[2 * e + 1] : 0u;
         const int c = ((int32_t)meta < 0) ? (int)((meta >> 16) & 0x7fffu) : 0;
@@ -176,9 +188,9 @@ qm_fit_long_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
         }
     }
     if (bad && nonfinite) atomicOr(nonfinite, 1);
-    lg_block_minmax(lo, hi, sh);
+    lg_block_minmax<LG_NT>(lo, hi, sh);
     const float scale = bm_scale_f32<LG_NB>(lo, hi);
-    const int total = lg_build(v, n, lo, scale, W, sh);
+    const int total = lg_build<LG_NT>(v, n, lo, scale, W, sh);
     const int n_lo = n - total;
     float* dst = state + c * state_ld + off[g] + n_lo;       // the values equal to the lower bound come first
     const uint32_t Wsa = bm_saddr(W);
@@ -199,7 +211,7 @@ qm_fit_long_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
     }
     __syncthreads();                                         // the record (global memory) is visible to the whole CTA
     const int lane = tid & 31;
-    lg_for_dirty_entries(W, sh,
+    lg_for_dirty_entries<LG_NT>(W, sh,
         [&](int start, int cnt) {
             float k[LG_SMALL];
 #pragma unroll
@@ -270,9 +282,9 @@ qm_predict_long_kernel(const PredictParams p) {
         }
     }
     if (bad && p.nonfinite) atomicOr(p.nonfinite, 1);
-    lg_block_minmax(lo, hi, sh);
+    lg_block_minmax<LG_NT>(lo, hi, sh);
     const float scale = bm_scale_f32<LG_NB>(lo, hi);
-    const int total = lg_build(v, n, lo, scale, W, sh);
+    const int total = lg_build<LG_NT>(v, n, lo, scale, W, sh);
     const int n_lo = n - total;
     auto emit = [&](int j, int rank) {
         double val = inverse_cdf<float>(rank, n, m, S, dn, dm, cu);
@@ -306,7 +318,7 @@ qm_predict_long_kernel(const PredictParams p) {
     __syncthreads();
     const int lane = tid & 31;
     auto key_at = [&](int at) -> float { return __ldg(X + (int64_t)rg[P2M[at]] * p.ld + c) + 0.0f; };
-    lg_for_dirty_entries(W, sh,
+    lg_for_dirty_entries<LG_NT>(W, sh,
         [&](int start, int cnt) {
             float k[LG_SMALL];
 #pragma unroll
@@ -336,6 +348,102 @@ qm_predict_long_kernel(const PredictParams p) {
         });
 }
 
+// ---------------------------------------------------------------- argsort of one series per cell
+// order[r * ld_order + c] = index of the r-th smallest value of x[t * row_stride + c], t = 0 .. n-1 (equal values in
+// index order).  Used to order a cell's analog training window and its query steps by the first predictor, which
+// is what lets the kNN search prune (analog_kernels.cu).  1024 threads, n <= 32 768.
+__global__ void __launch_bounds__(LG_NT_BIG, 1)
+series_argsort_kernel(const float* __restrict__ x, int64_t row_stride, int64_t C, int n,
+                      int32_t* __restrict__ order, int64_t ld_order, const uint8_t* __restrict__ valid) {
+    constexpr int NT = LG_NT_BIG;
+    using G = LgCfg<NT>;
+    extern __shared__ __align__(16) uint32_t lg_smem[];
+    uint32_t* W = lg_smem;
+    LgShared* sh = reinterpret_cast<LgShared*>(lg_smem + G::W_WORDS);
+    uint16_t* P2M = reinterpret_cast<uint16_t*>(lg_smem + G::W_WORDS + (sizeof(LgShared) + 3) / 4);   // position → member
+    const int64_t c = blockIdx.x;
+    if (valid && !valid[c]) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    float v[LG_E];
+    float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < LG_E; ++k) {
+        const int j = tid + k * NT;
+        v[k] = 0.0f;
+        if (j < n) {
+            v[k] = x[(int64_t)j * row_stride + c] + 0.0f;
+            lo = fminf(lo, v[k]); hi = fmaxf(hi, v[k]);
+        }
+    }
+    lg_block_minmax<NT>(lo, hi, sh);
+    const float scale = bm_scale_f32<G::NB>(lo, hi);
+    const int total = lg_build<NT>(v, n, lo, scale, W, sh);
+    const int n_lo = n - total;
+    auto emit = [&](int pos, int j) { order[(int64_t)pos * ld_order + c] = j; };
+    const uint32_t Wsa = bm_saddr(W);
+#pragma unroll
+    for (int b = 0; b < LG_E; b += 8) {
+        if (b * NT >= n) continue;                           // CTA-uniform
+        uint32_t q[8], dirty[8];
+        int on[8], pos[8], cur[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            q[u] = bm_bucket_f32<G::NB>(v[b + u], lo, scale);
+            on[u] = (v[b + u] > lo) ? n - (tid + (b + u) * NT) : 0;
+        }
+        bm_lookup_batch<8>(W, Wsa, q, on, pos, dirty, cur);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = tid + (b + u) * NT;
+            if (j < n) {
+                if (on[u] <= 0) P2M[atomicAdd(&sh->n_lo_cursor, 1u)] = (uint16_t)j;      // values at the lower bound (NaN too)
+                else if (!dirty[u]) emit(n_lo + pos[u], j);
+                else P2M[n_lo + pos[u] + cur[u]] = (uint16_t)j;
+            }
+        }
+    }
+    __syncthreads();
+    auto key_of = [&](int j) -> float { return __ldg(x + (int64_t)j * row_stride + c) + 0.0f; };
+    // members of one range of P2M in (key, index) order; keys are skipped for the lower-bound class (all equal)
+    auto order_small = [&](int first, int cnt, bool by_key) {
+        float k[LG_SMALL];
+        int m[LG_SMALL];
+#pragma unroll
+        for (int a = 0; a < LG_SMALL; ++a) { m[a] = (a < cnt) ? (int)P2M[first + a] : 0x7fffffff; k[a] = (a < cnt && by_key) ? key_of(m[a]) : 0.0f; }
+#pragma unroll
+        for (int a = 0; a < LG_SMALL; ++a) {
+            int r = 0;
+#pragma unroll
+            for (int b = 0; b < LG_SMALL; ++b)
+                if (b != a) r += (b < cnt && (k[b] < k[a] || (k[b] == k[a] && m[b] < m[a]))) ? 1 : 0;
+            if (a < cnt) emit(first + r, m[a]);
+        }
+    };
+    auto order_big = [&](int first, int cnt, bool by_key) {            // whole warp, one member per lane and round
+        for (int a = lane; a < cnt; a += 32) {
+            const int ma = (int)P2M[first + a];
+            const float ka = by_key ? key_of(ma) : 0.0f;
+            int r = 0;
+            for (int b = 0; b < cnt; ++b) {
+                const int mb = (int)P2M[first + b];
+                const float kb = by_key ? key_of(mb) : 0.0f;
+                r += (kb < ka || (kb == ka && mb < ma)) ? 1 : 0;
+            }
+            emit(first + r, ma);
+        }
+    };
+    lg_for_dirty_entries<NT>(W, sh, [&](int start, int cnt) { order_small(n_lo + start, cnt, true); },
+                             [&](int start, int cnt) { order_big(n_lo + start, cnt, true); });
+    if (tid < 32) {                                          // the lower-bound class: equal keys, index order
+        if (n_lo <= LG_SMALL) { if (lane == 0 && n_lo > 0) order_small(0, n_lo, false); }
+        else order_big(0, n_lo, false);
+    }
+}
+
+constexpr size_t lg_argsort_smem() {
+    return (size_t)LgCfg<LG_NT_BIG>::W_WORDS * 4 + ((sizeof(LgShared) + 3) / 4) * 4 + (size_t)LgCfg<LG_NT_BIG>::NMAX * 2;
+}
+
 constexpr size_t lg_fit_smem() { return (size_t)LG_W_WORDS * 4 + sizeof(LgShared); }
 constexpr size_t lg_predict_smem() { return (size_t)LG_W_WORDS * 4 + ((sizeof(LgShared) + 3) / 4) * 4 + (size_t)LG_NMAX * 2; }
 
@@ -359,3 +467,21 @@ int qm_predict_long(const PredictParams& p, cudaStream_t st) {
 }
 
 }  // namespace sdb
+
+using namespace sdb;
+
+extern "C" int sdb_series_argsort(const void* x, int dtype, int64_t row_stride, int64_t n_cells, int n_steps,
+                                  int32_t* order, int64_t ld_order, const uint8_t* cell_valid, void* stream) {
+    if (!x || !order) return sdb_fail(SDB_E_INVALID, "sdb_series_argsort: NULL pointer");
+    if (n_cells <= 0 || n_steps <= 0 || row_stride < n_cells || ld_order < n_cells) return sdb_fail(SDB_E_INVALID, "sdb_series_argsort: bad shape");
+    if (dtype != SDB_F32) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_series_argsort: float32 only");
+    if (n_steps > LgCfg<LG_NT_BIG>::NMAX) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_series_argsort: at most %d steps", LgCfg<LG_NT_BIG>::NMAX);
+    auto kern = series_argsort_kernel;
+    SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lg_argsort_smem()));
+    kern<<<(unsigned)n_cells, LG_NT_BIG, lg_argsort_smem(), (cudaStream_t)stream>>>((const float*)x, row_stride, n_cells, n_steps,
+                                                                                  order, ld_order, cell_valid);
+    SDB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int sdb_series_argsort_max_steps(void) { return LgCfg<LG_NT_BIG>::NMAX; }

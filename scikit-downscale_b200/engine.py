@@ -346,9 +346,18 @@ def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, r
     return (out, rank) if want_rank else out
 
 
+def series_argsort(x: torch.Tensor, row_stride: int, n_steps: int, n_cells: int, valid=None) -> torch.Tensor:
+    """Per cell, the time steps in ascending order of ``x[t * row_stride + c]`` → int32 ``[n_steps, n_cells]``."""
+    lib = _lib.load()
+    order = torch.empty((n_steps, n_cells), dtype=torch.int32, device=x.device)
+    _lib.check(lib.sdb_series_argsort(_ptr(x), _code(x), row_stride, n_cells, n_steps, _ptr(order), n_cells, _ptr(valid),
+                                      _stream()), 'sdb_series_argsort')
+    return order
+
+
 def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_query: torch.Tensor, k: int, *,
                    thresh=None, rand_idx=None, out_dtype=None, want_idx: bool = False, valid=None,
-                   nonfinite=None, logistic_C: float = 1.0):
+                   nonfinite=None, logistic_C: float = 1.0, prune: bool | None = None, order_train=None):
     """PureAnalog / AnalogRegression fit+predict for all cells (gard.py:58-87, 152-224, 273-364).
 
     X_train [T, p, C], y_train [T, C], X_query [Tq, p, C] → out [Tq, 3, C]."""
@@ -371,11 +380,25 @@ def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_qu
     idx = torch.empty((Tq, k, C), dtype=torch.int32, device=dev) if want_idx else None
     if rand_idx is not None:
         rand_idx = torch.as_tensor(np.ascontiguousarray(rand_idx, dtype=np.int32)).to(dev)
-    _lib.check(lib.sdb_analog_predict(kind, _ptr(X_train), _ptr(y_train), _ptr(X_query), _code(X_train), C, C,
-                                      T, Tq, p, k, int(thresh is not None),
-                                      float(thresh) if thresh is not None else 0.0, float(logistic_C), _ptr(rand_idx),
-                                      _ptr(out), _TORCH_CODE[od], C, _ptr(idx), _ptr(valid), _ptr(nonfinite),
-                                      _stream()), 'sdb_analog_predict')
+    # exact pruning needs both windows ordered by the first predictor: float32, at most 32 768 steps, and enough
+    # training rows for the ordered walk to pay for the two argsorts
+    max_steps = lib.sdb_series_argsort_max_steps()
+    can_prune = X_train.dtype == torch.float32 and T <= max_steps and Tq <= max_steps
+    if prune is None:
+        prune = can_prune and T >= 2048 and os.environ.get('SDB_ANALOG_PRUNE', '1') != '0'
+    if prune and not can_prune:
+        raise ValueError('pruned analog search needs float32 inputs of at most %d steps' % max_steps)
+    args = (kind, _ptr(X_train), _ptr(y_train), _ptr(X_query), _code(X_train), C, C, T, Tq, p, k, int(thresh is not None),
+            float(thresh) if thresh is not None else 0.0, float(logistic_C), _ptr(rand_idx),
+            _ptr(out), _TORCH_CODE[od], C, _ptr(idx), _ptr(valid), _ptr(nonfinite))
+    if prune:
+        if order_train is None:
+            order_train = series_argsort(X_train, p * C, T, C, valid)
+        order_query = series_argsort(X_query, p * C, Tq, C, valid)
+        _lib.check(lib.sdb_analog_predict_pruned(*args, _ptr(order_train), _ptr(order_query), C, _stream()),
+                   'sdb_analog_predict_pruned')
+    else:
+        _lib.check(lib.sdb_analog_predict(*args, _stream()), 'sdb_analog_predict')
     return (out, idx) if want_idx else out
 
 
