@@ -245,20 +245,37 @@ int sdb_analog_predict(int kind, const void* X_train, const void* y_train, const
                        const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
 
 /*
- * The same search with exact pruning (float32 inputs): order_train [t_fit, ld_order] / order_query [t_query,
- * ld_order] list, per cell, the training rows / query steps in ascending order of the FIRST predictor
- * (sdb_series_argsort on X_train[:, 0, :] and X_query[:, 0, :] with row_stride = n_features * ld).  A CTA's 256
- * consecutive queries of that order then only visit the training chunks whose first-predictor gap can still beat
- * their current k-th distance.  Identical results (neighbours, order, outputs) — the reference prunes the same
- * search with sklearn's KDTree, gard.py:82,194,299.
+ * The spatial index of the analog search, for all cells at once — the counterpart of AnalogBase.fit's KDTree
+ * (gard.py:82).  Every series' training rows are cut into up to sdb_analog_grid_boxes() = 512 boxes by quantile
+ * planes of the first predictors (1 predictor: 512 slabs, 2: 22 x 22, 3: 8 x 8 x 8).
+ *   sdb_analog_grid_fit     X_train [t_fit, p, ld] → bounds [sdb_analog_grid_planes() = 511, ld_grid] (the planes),
+ *                           perm_train [t_fit, ld_grid] (rows grouped by box), box_start [513, ld_grid];
+ *                           workspace: int32 [t_fit, ld_grid] scratch.  float32, 64 <= t_fit <= 32768.
+ *   sdb_analog_grid_assign  X_query → perm_query [t_query, ld_grid]: the query steps grouped by the SAME boxes, which
+ *                           hands neighbouring queries to the same warp.
+ * sdb_analog_predict_pruned is sdb_analog_predict with these tables: ONE CTA per cell stages the box-ordered
+ * training window once into shared memory (float32) and every query walks the boxes shell by shell around its own,
+ * skipping boxes whose distance lower bound exceeds its k-th best distance and stopping when the next shell is out
+ * of reach.  Identical results (neighbours, order, outputs; exact distance ties → lowest training row).  Covers
+ * what sdb_analog_pruned_supported() reports: float32, 1..3 predictors, k <= 16, t_fit <= 18 958 (3 predictors).
  */
+int sdb_analog_grid_fit(const void* X_train, int dtype, int64_t ld, int64_t n_cells, int t_fit, int n_features,
+                        int32_t* workspace, float* bounds, int32_t* perm_train, int32_t* box_start, int64_t ld_grid,
+                        const uint8_t* cell_valid, void* stream);
+int sdb_analog_grid_assign(const void* X_query, int dtype, int64_t ld, int64_t n_cells, int t_query, int n_features,
+                           const float* bounds, int32_t* perm_query, int64_t ld_grid,
+                           const uint8_t* cell_valid, void* stream);
+int sdb_analog_grid_boxes(void);
+int sdb_analog_grid_planes(void);
+int sdb_analog_pruned_supported(int dtype, int t_fit, int n_features, int k);
 int sdb_analog_predict_pruned(int kind, const void* X_train, const void* y_train, const void* X_query,
                               int dtype, int64_t ld, int64_t n_cells,
                               int t_fit, int t_query, int n_features, int k,
                               int has_thresh, double thresh, double logistic_c, const int32_t* rand_idx,
                               void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
                               const uint8_t* cell_valid, int32_t* nonfinite,
-                              const int32_t* order_train, const int32_t* order_query, int64_t ld_order, void* stream);
+                              const int32_t* perm_train, const int32_t* perm_query, const int32_t* box_start,
+                              const float* bounds, int64_t ld_grid, void* stream);
 
 /*
  * order[r * ld_order + c] = index t of the r-th smallest x[t * row_stride + c], t = 0 .. n_steps - 1, for every cell

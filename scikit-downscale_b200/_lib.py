@@ -72,7 +72,14 @@ SIGNATURES = {
                                           c_int, c_double, c_double, c_void_p,
                                           c_void_p, c_int, c_int64, c_void_p,
                                           c_void_p, c_void_p,
-                                          c_void_p, c_void_p, c_int64, c_void_p]),
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'sdb_analog_grid_fit': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_int64, c_void_p, c_void_p]),
+    'sdb_analog_grid_assign': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64,
+                                       c_void_p, c_void_p]),
+    'sdb_analog_pruned_supported': (c_int, [c_int, c_int, c_int, c_int]),
+    'sdb_analog_grid_boxes': (c_int, []),
+    'sdb_analog_grid_planes': (c_int, []),
     'sdb_series_argsort': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     'sdb_series_argsort_max_steps': (c_int, []),
     'sdb_series_rank': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,

@@ -17,15 +17,6 @@
 // (float64, broadcast reads).  The work is FP64-pipe bound — there is no GEMM here (K = p
 // is 1..8 and the `|a|^2 - 2ab + |b|^2` trick would break index exactness), so no tensor
 // cores.
-//
-// Pruning (round 2; the reference prunes with a KD-tree, gard.py:82,194,299): with both the training rows and the
-// query steps of a cell ordered by the first predictor, a CTA's 256 queries sit in a narrow slab of x0.  The CTA
-// starts at the training chunk around that slab and walks outwards in both directions; a direction stops when
-// (x0 of the chunk edge - q0)^2 > current k-th best distance for EVERY query of the CTA — no point beyond can
-// enter any list, because a squared distance is never smaller than its first term (float64 additions of
-// non-negative terms are monotone).  Exact: same neighbours, same order; ties are broken by the lower training
-// index explicitly, since the scan no longer visits rows in index order.  About one training point in eight is
-// visited for 3 standard-normal predictors, k = 10, 30 years of days.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cmath>
@@ -33,6 +24,7 @@
 #include "../../include/sdb.h"
 #include "common.cuh"
 #include "np_pairwise.cuh"
+#include "analog_grid.cuh"
 
 namespace sdb {
 
@@ -49,9 +41,8 @@ struct AnalogParams {
     int has_thresh; double thresh; double logistic_c; const int32_t* rand_idx;
     void* out; int out_f64; int64_t ld_out; int32_t* knn_idx;
     const uint8_t* valid; int32_t* nonfinite;
-    // pruned search (float32 inputs): training rows / query steps of every cell in ascending order of the FIRST
-    // predictor (sdb_series_argsort); NULL = brute force over the whole window
-    const int32_t* ord_t; const int32_t* ord_q; int64_t ld_ord;
+    // pruned search (analog_cell_kernel): the quantile grid of every cell's training window (analog_grid.cu)
+    const int32_t* perm_t; const int32_t* perm_q; const int32_t* box_start; const float* bounds; int64_t ld_grid;
 };
 
 __device__ __forceinline__ void store3(const AnalogParams& a, int q, int64_t c, double pred, double prob, double err) {
@@ -431,10 +422,8 @@ analog_kernel(const AnalogParams a) {
     const int k = a.k;
     const T* Xtr = (const T*)a.Xtr;
     const T* Xq = (const T*)a.Xq;
-    const bool pruned = a.ord_t != nullptr;
-    const int qs = tile * AN_THREADS + threadIdx.x;   // position in the CTA's query order
-    const bool live = qs < a.t_query;
-    const int q = (live && pruned) ? a.ord_q[(int64_t)qs * a.ld_ord + c] : qs;
+    const int q = tile * AN_THREADS + threadIdx.x;
+    const bool live = q < a.t_query;
     // the query point: float32 inputs are held as float32 only (the exact float64 value is its
     // widening), float64 inputs as float64
     double xq64[FILTER ? 1 : P];
@@ -455,10 +444,7 @@ analog_kernel(const AnalogParams a) {
 #pragma unroll
     for (int i = 0; i < (KREG > 0 ? KREG : 1); ++i) { bd[i] = INFINITY; bi[i] = -1; }
     if (KREG == 0) for (int i = 0; i < k; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
-    double worst = INFINITY;                          // current k-th best distance ...
-    int worst_i = 0x7fffffff;                         // ... and the training row that holds it
-    // (distance, training row) order: the lower row wins an exact distance tie whatever order rows are visited in
-    auto lt = [](double d, int id, double d2, int id2) -> bool { return d < d2 || (d == d2 && id < id2); };
+    double worst = INFINITY;                          // current k-th best distance
     float worstf = live ? INFINITY : -1.0f;           // float32 upper bound of it (relative slack 1e-6 >> float32 error); lanes without a query never pass
     int qn = 0;                                       // candidates parked in this lane's queue
 
@@ -469,23 +455,22 @@ analog_kernel(const AnalogParams a) {
             if (i < qn) {
                 const double d = qd[i * AN_THREADS + threadIdx.x];
                 const int id = qi[i * AN_THREADS + threadIdx.x];
-                if (lt(d, id, worst, worst_i)) {
-                    // branch-free insertion into the register list, ascending by (distance, training row)
+                if (d < worst) {
+                    // branch-free insertion into the register list (strict < keeps the earlier index first on ties)
 #pragma unroll
                     for (int j = (KREG > 0 ? KREG : 1) - 1; j > 0; --j) {
-                        const bool shift = lt(d, id, bd[j - 1], bi[j - 1]);
-                        const bool here = !shift && lt(d, id, bd[j], bi[j]);
+                        const bool shift = d < bd[j - 1];
+                        const bool here = !shift && (d < bd[j]);
                         const double nd = shift ? bd[j - 1] : (here ? d : bd[j]);
                         const int ni = shift ? bi[j - 1] : (here ? id : bi[j]);
                         bd[j] = nd; bi[j] = ni;
                     }
-                    if (lt(d, id, bd[0], bi[0])) { bd[0] = d; bi[0] = id; }
+                    if (d < bd[0]) { bd[0] = d; bi[0] = id; }
                     // k may be smaller than KREG: the k-th entry is the acceptance bound
                     double w = bd[(KREG > 0 ? KREG : 1) - 1];
-                    int wi = bi[(KREG > 0 ? KREG : 1) - 1];
 #pragma unroll
-                    for (int j = 0; j < (KREG > 0 ? KREG : 1); ++j) if (j == k - 1) { w = bd[j]; wi = bi[j]; }
-                    worst = w; worst_i = (wi < 0) ? 0x7fffffff : wi;
+                    for (int j = 0; j < (KREG > 0 ? KREG : 1); ++j) if (j == k - 1) w = bd[j];
+                    worst = w;
                 }
             }
         }
@@ -493,19 +478,14 @@ analog_kernel(const AnalogParams a) {
         qn = 0;
     };
 
-    __shared__ int cid[AN_CHUNK];                     // training row of every staged point
-    __shared__ int s_pos;
-    auto process = [&](int t0) {
+    for (int t0 = 0; t0 < a.t_fit; t0 += AN_CHUNK) {
         const int nt = min(AN_CHUNK, a.t_fit - t0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < nt; t += AN_THREADS)
-            cid[t] = pruned ? a.ord_t[(int64_t)(t0 + t) * a.ld_ord + c] : t0 + t;
         __syncthreads();
         for (int i = threadIdx.x; i < nt * p; i += AN_THREADS) {
             const int t = i / p, f = i - t * p;
-            const T raw = Xtr[((int64_t)cid[t] * a.p + f) * a.ld + c];
+            const T raw = Xtr[((int64_t)(t0 + t) * a.p + f) * a.ld + c];
             const double xv = (double)raw;
-            if (a.nonfinite && (tile == 0 || pruned) && !isfinite(xv)) atomicOr(a.nonfinite, 1);
+            if (a.nonfinite && tile == 0 && !isfinite(xv)) atomicOr(a.nonfinite, 1);
             chunk[t * P + f] = xv;
             if (FILTER) chunkf[t * PF + f] = (float)raw;
         }
@@ -522,7 +502,7 @@ analog_kernel(const AnalogParams a) {
             }
         }
         __syncthreads();
-        if (KREG == 0 && !live) return;
+        if (KREG == 0 && !live) continue;
         // exact float64 distance of training point t (same operation order as the reference's KDTree)
         auto exact_d = [&](int t) -> double {
             double d = 0.0;
@@ -533,7 +513,7 @@ analog_kernel(const AnalogParams a) {
             return d;
         };
         auto accept = [&](int t, double d) {
-            const int id = cid[t];
+            const int id = t0 + t;
             if (KREG > 0) {
                 // park the candidate: the (long, branch-free) list insertion runs for the whole warp,
                 // so it is batched — one pass inserts up to one candidate for every lane
@@ -556,7 +536,7 @@ analog_kernel(const AnalogParams a) {
                     pos = big;
                 }
                 bd[pos] = d; bi[pos] = id;
-                worst = bd[0]; worst_i = bi[0];
+                worst = bd[0];
                 worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
             }
         };
@@ -588,7 +568,7 @@ analog_kernel(const AnalogParams a) {
                         }
                         if (d32 <= worstf) {
                             const double d = exact_d(t);
-                            if (lt(d, cid[t], worst, worst_i)) accept(t, d);
+                            if (d < worst) accept(t, d);
                         }
                     }
                 }
@@ -603,68 +583,12 @@ analog_kernel(const AnalogParams a) {
                     const int t = tb + u;
                     if (t < nt && live) {
                         const double d = exact_d(t);
-                        if (lt(d, cid[t], worst, worst_i)) accept(t, d);
+                        if (d < worst) accept(t, d);
                     }
                 }
                 if (KREG > 0) {
                     if (__any_sync(0xffffffffu, qn > AN_QD - 4)) drain();
                 }
-            }
-        }
-    };
-    if (!pruned) {
-        for (int t0 = 0; t0 < a.t_fit; t0 += AN_CHUNK) process(t0);
-    } else {
-        // ---- pruned traversal: start at the chunk around the CTA's middle query, walk outwards
-        const int n_chunks = (a.t_fit + AN_CHUNK - 1) / AN_CHUNK;
-        auto x0_sorted = [&](int t) -> float { return (float)Xtr[((int64_t)a.ord_t[(int64_t)t * a.ld_ord + c] * a.p) * a.ld + c]; };
-        if (threadIdx.x < 32) {
-            const int lane = threadIdx.x;
-            const int qmid = min(tile * AN_THREADS + AN_THREADS / 2, a.t_query - 1);
-            const float xt = (float)Xq[((int64_t)a.ord_q[(int64_t)qmid * a.ld_ord + c] * a.p) * a.ld + c];
-            int lo = 0, hi = a.t_fit;                 // number of training points with x0 <= xt lies in [lo, hi]
-            while (lo < hi) {
-                const int step = (hi - lo + 31) >> 5;
-                const int probe = lo + lane * step;
-                const bool le = probe < hi && x0_sorted(probe) <= xt;
-                const int j = __popc(__ballot_sync(0xffffffffu, le));      // probes 0 .. j-1 are <= xt (x0 ascends)
-                const int nlo = j ? lo + (j - 1) * step + 1 : lo;
-                const int nhi = (j < 32 && lo + j * step < hi) ? lo + j * step : hi;
-                lo = nlo; hi = nhi;
-            }
-            if (lane == 0) s_pos = lo;
-        }
-        __syncthreads();
-        const int c0 = min(max(s_pos / AN_CHUNK, 0), n_chunks - 1);
-        const double q0 = xqv(0);
-        // edges of the processed range, read from the staged float32 copy (first / last point of a sorted chunk)
-        auto edge_lo = [&]() -> double { return (double)chunkf[0]; };
-        auto edge_hi = [&](int t0) -> double { return (double)chunkf[(min(AN_CHUNK, a.t_fit - t0) - 1) * PF]; };
-        process(c0 * AN_CHUNK);
-        if (KREG > 0) drain();
-        double el = edge_lo(), er = edge_hi(c0 * AN_CHUNK);
-        int left = c0 - 1, right = c0 + 1;
-        bool go_l = left >= 0, go_r = right < n_chunks;
-        while (go_l || go_r) {
-            if (go_r) {
-                const double dx = er - q0;            // every point further right has x0 >= er
-                const bool need = live && (dx <= 0.0 || dx * dx <= worst);
-                if (__syncthreads_or(need)) {
-                    process(right * AN_CHUNK);
-                    if (KREG > 0) drain();
-                    er = edge_hi(right * AN_CHUNK);
-                    go_r = ++right < n_chunks;
-                } else go_r = false;
-            }
-            if (go_l) {
-                const double dx = q0 - el;            // every point further left has x0 <= el
-                const bool need = live && (dx <= 0.0 || dx * dx <= worst);
-                if (__syncthreads_or(need)) {
-                    process(left * AN_CHUNK);
-                    if (KREG > 0) drain();
-                    el = edge_lo();
-                    go_l = --left >= 0;
-                } else go_l = false;
             }
         }
     }
@@ -747,6 +671,215 @@ static int dispatch_analog(const AnalogParams& a, cudaStream_t st) {
         case 4: return launch_analog<T, 4>(a, st);
         default: return launch_analog<T, AN_PMAX>(a, st);
     }
+}
+
+
+// ---------------------------------------------------------------- pruned search: one CTA per cell (round 2)
+// The reference prunes its search with a per-cell KDTree (gard.py:82,194,299); the brute-force kernel above
+// re-stages the whole training window for every 256 queries and evaluates all T_fit distances per query.  Here
+//   * ONE CTA owns a cell: its training window, ordered by the boxes of a quantile grid (analog_grid.cu; up to 512
+//     boxes of ~T/512 rows), is staged ONCE into shared memory as float32 (12 bytes per row for 3 predictors:
+//     18 250 rows = 219 KB) and serves all of the cell's queries;
+//   * one thread = one query at a time.  It visits the boxes shell by shell around its own box (index distance
+//     0, 1, 2, ...), skipping boxes whose lower bound sum_f gap_f^2 exceeds its current k-th best distance, and stops
+//     when the nearest plane of the next shell is farther than that distance — nothing beyond can enter the list.
+//     Bounds and distances are float64 sums of squares taken in the same order (f = 0, 1, 2), and float64
+//     additions / squares of non-negative terms are monotone, so bound <= distance holds in floating point:
+//     the result is EXACT (same neighbours, same order as the brute force; the lower training row wins a tie);
+//   * distances are screened in float32 and re-evaluated in float64 from the same float32 values (the exact
+//     widening of the inputs — what the reference's float64 KDTree sees).
+// About 1 row in 15 is visited for 3 standard-normal predictors, k = 10, 30 years of days.
+constexpr int AC_THREADS = 512;
+constexpr int AC_K = 16;             // neighbours kept in registers
+
+template <int P> constexpr size_t ac_smem_bytes(int t_fit) {
+    return (size_t)t_fit * P * 4 + (size_t)(AG_BOXES + 1) * 4 + (size_t)AG_NBND * 4 + 16;
+}
+
+template <int P, bool LOGIT>
+__global__ void __launch_bounds__(AC_THREADS, 1)
+analog_cell_kernel(const AnalogParams a) {
+    extern __shared__ __align__(16) float ac_smem[];
+    const int T = a.t_fit;
+    float* pts = ac_smem;                                           // [T][P], box order
+    int* bstart = reinterpret_cast<int*>(ac_smem + (size_t)T * P);  // [AG_BOXES + 1]
+    float* planes = reinterpret_cast<float*>(bstart + AG_BOXES + 1);
+    const int64_t c = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (a.valid && !a.valid[c]) {
+        for (int q = tid; q < a.t_query; q += AC_THREADS) store3(a, q, c, NAN, NAN, NAN);
+        return;
+    }
+    const float* Xtr = (const float*)a.Xtr;
+    const float* Xq = (const float*)a.Xq;
+    int g[3];
+    ag_dims(P, g);
+    const int nplanes = (g[0] - 1) + (g[1] - 1) + (g[2] - 1);
+    const int nbox = g[0] * g[1] * g[2];
+    for (int i = tid; i < nplanes; i += AC_THREADS) planes[i] = a.bounds[(int64_t)i * a.ld_grid + c];
+    for (int i = tid; i <= AG_BOXES; i += AC_THREADS) bstart[i] = a.box_start[(int64_t)i * a.ld_grid + c];
+    bool bad = false;
+    for (int i = tid; i < T; i += AC_THREADS) {
+        const int row = a.perm_t[(int64_t)i * a.ld_grid + c];
+#pragma unroll
+        for (int f = 0; f < P; ++f) {
+            const float v = Xtr[((int64_t)row * P + f) * a.ld + c];
+            bad |= !isfinite(v);
+            pts[(size_t)i * P + f] = v;
+        }
+    }
+    if (bad && a.nonfinite) atomicOr(a.nonfinite, 1);
+    __syncthreads();
+    const float* pl[3] = {planes, planes + (g[0] - 1), planes + (g[0] - 1) + (g[1] - 1)};
+    const int k = a.k;
+    auto row_of = [&](int pos) -> int { return a.perm_t[(int64_t)pos * a.ld_grid + c]; };
+
+    for (int qs = tid; qs < a.t_query; qs += AC_THREADS) {
+        const int q = a.perm_q[(int64_t)qs * a.ld_grid + c];
+        float xqf[P];
+        bool qbad = false;
+#pragma unroll
+        for (int f = 0; f < P; ++f) { xqf[f] = Xq[((int64_t)q * P + f) * a.ld + c]; qbad |= !isfinite(xqf[f]); }
+        if (qbad && a.nonfinite) atomicOr(a.nonfinite, 1);
+        int qb[3] = {0, 0, 0};
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+            if (f < P && g[f] > 1) qb[f] = ag_slab(xqf[f], pl[f], g[f]);
+        // neighbour list: ascending by (distance, training row); bpos = position in box order, row fetched on demand
+        double bd[AC_K];
+        int bpos[AC_K];
+#pragma unroll
+        for (int i = 0; i < AC_K; ++i) { bd[i] = INFINITY; bpos[i] = -1; }
+        double worst = INFINITY;
+        int worst_pos = -1;
+        float worstf = INFINITY;
+        auto before = [&](double d, int pos, double d2, int pos2) -> bool {      // (d, row(pos)) < (d2, row(pos2))
+            if (d != d2) return d < d2;
+            if (pos2 < 0) return true;
+            return row_of(pos) < row_of(pos2);
+        };
+        auto insert = [&](double d, int pos) {
+#pragma unroll
+            for (int j = AC_K - 1; j > 0; --j) {
+                const bool shift = before(d, pos, bd[j - 1], bpos[j - 1]);
+                const bool here = !shift && before(d, pos, bd[j], bpos[j]);
+                const double nd = shift ? bd[j - 1] : (here ? d : bd[j]);
+                const int np = shift ? bpos[j - 1] : (here ? pos : bpos[j]);
+                bd[j] = nd; bpos[j] = np;
+            }
+            if (before(d, pos, bd[0], bpos[0])) { bd[0] = d; bpos[0] = pos; }
+            double w = bd[AC_K - 1];
+            int wp = bpos[AC_K - 1];
+#pragma unroll
+            for (int j = 0; j < AC_K; ++j) if (j == k - 1) { w = bd[j]; wp = bpos[j]; }
+            worst = w; worst_pos = wp;
+            worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
+        };
+        auto gap = [&](int f, int b) -> double {      // distance of q_f to slab b of predictor f: rows there satisfy plane[b-1] <= x < plane[b]
+            const double qf = (double)xqf[f < P ? f : 0];
+            const double lo = (b > 0) ? (double)pl[f][b - 1] : -INFINITY;
+            const double hi = (b < g[f] - 1) ? (double)pl[f][b] : INFINITY;
+            return qf < lo ? lo - qf : (qf > hi ? qf - hi : 0.0);
+        };
+        auto scan_box = [&](int box) {
+            const int r0 = bstart[box], r1 = bstart[box + 1];
+            for (int t = r0; t < r1; ++t) {
+                const float* x = pts + (size_t)t * P;
+                const float d0 = xqf[0] - x[0];
+                float d32 = d0 * d0;
+                if (P > 1) { const float d1 = xqf[1] - x[1]; d32 = fmaf(d1, d1, d32); }
+                if (P > 2) { const float d2 = xqf[2] - x[2]; d32 = fmaf(d2, d2, d32); }
+                if (d32 <= worstf) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int f = 0; f < P; ++f) { const double tmp = (double)xqf[f] - (double)x[f]; d += tmp * tmp; }
+                    if (before(d, t, worst, worst_pos)) insert(d, t);
+                }
+            }
+        };
+        const int rmax = max(g[0], max(g[1], g[2]));
+        for (int r = 0; r < rmax; ++r) {
+            const int r1 = g[1] > 1 ? r : 0, r2 = g[2] > 1 ? r : 0;
+            for (int d0 = -r; d0 <= r; ++d0) {
+                const int b0 = qb[0] + d0;
+                if (b0 < 0 || b0 >= g[0]) continue;
+                const double t0 = gap(0, b0);
+                const double l0 = t0 * t0;
+                if (l0 > worst) continue;
+                for (int d1 = -r1; d1 <= r1; ++d1) {
+                    const int b1 = qb[1] + d1;
+                    if (b1 < 0 || b1 >= g[1]) continue;
+                    double l1 = l0;
+                    if (g[1] > 1) { const double t1 = gap(1, b1); l1 += t1 * t1; }
+                    if (l1 > worst) continue;
+                    const bool edge01 = (d0 == -r || d0 == r || (g[1] > 1 && (d1 == -r || d1 == r)));
+                    // boxes of this shell: index distance exactly r in at least one predictor
+                    const int step2 = (edge01 || r2 == 0) ? 1 : 2 * r2;
+                    for (int d2 = -r2; d2 <= r2; d2 += step2) {
+                        if (!edge01 && g[2] > 1 && d2 != -r && d2 != r) continue;
+                        if (!edge01 && g[2] == 1 && r > 0) continue;
+                        const int b2 = qb[2] + d2;
+                        if (b2 < 0 || b2 >= g[2]) continue;
+                        double l2 = l1;
+                        if (g[2] > 1) { const double t2 = gap(2, b2); l2 += t2 * t2; }
+                        if (l2 > worst) continue;
+                        scan_box((b0 * g[1] + b1) * g[2] + b2);
+                    }
+                }
+            }
+            // every unvisited box is at index distance >= r + 1 along some predictor: its gap there is at least the
+            // distance to the nearest plane of that shell
+            double gmin = INFINITY;
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                if (g[f] > 1) {
+                    const double qf = (double)xqf[f < P ? f : 0];
+                    if (qb[f] - r - 1 >= 0) gmin = fmin(gmin, fmax(qf - (double)pl[f][qb[f] - r - 1], 0.0));
+                    if (qb[f] + r + 1 <= g[f] - 1) gmin = fmin(gmin, fmax((double)pl[f][qb[f] + r] - qf, 0.0));
+                }
+            }
+            if (!(gmin * gmin <= worst)) break;
+        }
+        // rows of the neighbours, then the model's statistic
+        int li[AC_K];
+        double ld2[AC_K];
+#pragma unroll
+        for (int i = 0; i < AC_K; ++i) { li[i] = (i < k && bpos[i] >= 0) ? row_of(bpos[i]) : 0; ld2[i] = bd[i]; }
+        if (a.knn_idx) {
+#pragma unroll
+            for (int i = 0; i < AC_K; ++i) if (i < k) a.knn_idx[((int64_t)q * k + i) * a.C + c] = li[i];
+        }
+        auto idx = [&](int i) -> int { return li[i]; };
+        auto dist2 = [&](int i) -> double { return ld2[i]; };
+        double xq[P];
+#pragma unroll
+        for (int f = 0; f < P; ++f) xq[f] = (double)xqf[f];
+        if (LOGIT || a.kind == SDB_ANALOG_REGRESSION) regression_epilogue<float, P, LOGIT>(a, q, c, k, idx, xq);
+        else pure_analog_epilogue<float>(a, q, c, k, idx, dist2);
+    }
+}
+
+template <int P>
+static int launch_analog_cell(const AnalogParams& a, cudaStream_t st) {
+    const size_t smem = ac_smem_bytes<P>(a.t_fit);
+    const bool logit = (a.kind == SDB_ANALOG_REGRESSION) && a.has_thresh;
+    if (logit) {
+        auto kern = analog_cell_kernel<P, true>;
+        SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)a.C, AC_THREADS, smem, st>>>(a);
+    } else {
+        auto kern = analog_cell_kernel<P, false>;
+        SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)a.C, AC_THREADS, smem, st>>>(a);
+    }
+    SDB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// largest training window the per-cell kernel can stage (227 KB of shared memory per CTA)
+static int analog_cell_max_steps(int p) {
+    const size_t fixed = (size_t)(AG_BOXES + 1) * 4 + (size_t)AG_NBND * 4 + 16;
+    return (int)((232448 - fixed) / ((size_t)p * 4));
 }
 
 // ---------------------------------------------------------------- PureRegression (gard.py:367-504)
@@ -982,7 +1115,8 @@ static int analog_predict_impl(int kind, const void* X_train, const void* y_trai
                                   int has_thresh, double thresh, double logistic_c, const int32_t* rand_idx,
                                   void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
                                   const uint8_t* cell_valid, int32_t* nonfinite,
-                                  const int32_t* order_train, const int32_t* order_query, int64_t ld_order, void* stream) {
+                                  const int32_t* perm_train, const int32_t* perm_query, const int32_t* box_start, const float* bounds,
+                                  int64_t ld_grid, void* stream) {
     if (!X_train || !y_train || !X_query || !out) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: NULL pointer");
     if (n_cells <= 0 || t_fit <= 0 || t_query <= 0 || ld < n_cells || ld_out < n_cells)
         return sdb_fail(SDB_E_INVALID, "sdb_analog_predict: bad shape");
@@ -999,8 +1133,15 @@ static int analog_predict_impl(int kind, const void* X_train, const void* y_trai
     a.has_thresh = has_thresh; a.thresh = thresh; a.logistic_c = logistic_c; a.rand_idx = rand_idx;
     a.out = out; a.out_f64 = (out_dtype == SDB_F64); a.ld_out = ld_out; a.knn_idx = knn_idx;
     a.valid = cell_valid; a.nonfinite = nonfinite;
-    a.ord_t = order_train; a.ord_q = order_query; a.ld_ord = ld_order;
+    a.perm_t = perm_train; a.perm_q = perm_query; a.box_start = box_start; a.bounds = bounds; a.ld_grid = ld_grid;
     cudaStream_t st = (cudaStream_t)stream;
+    if (perm_train) {
+        switch (n_features) {
+            case 1: return launch_analog_cell<1>(a, st);
+            case 2: return launch_analog_cell<2>(a, st);
+            default: return launch_analog_cell<3>(a, st);
+        }
+    }
     return dtype == SDB_F32 ? dispatch_analog<float>(a, st) : dispatch_analog<double>(a, st);
 }
 
@@ -1011,7 +1152,15 @@ extern "C" int sdb_analog_predict(int kind, const void* X_train, const void* y_t
                                   void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
                                   const uint8_t* cell_valid, int32_t* nonfinite, void* stream) {
     return analog_predict_impl(kind, X_train, y_train, X_query, dtype, ld, n_cells, t_fit, t_query, n_features, k, has_thresh, thresh,
-                               logistic_c, rand_idx, out, out_dtype, ld_out, knn_idx, cell_valid, nonfinite, nullptr, nullptr, 0, stream);
+                               logistic_c, rand_idx, out, out_dtype, ld_out, knn_idx, cell_valid, nonfinite,
+                               nullptr, nullptr, nullptr, nullptr, 0, stream);
+}
+
+// which (n_features, k, t_fit) the pruned per-cell search covers: 1..3 predictors, k <= 16, the window must fit in
+// shared memory (18 958 steps for 3 predictors); 0 = use sdb_analog_predict
+extern "C" int sdb_analog_pruned_supported(int dtype, int t_fit, int n_features, int k) {
+    return dtype == SDB_F32 && n_features >= 1 && n_features <= 3 && k >= 1 && k <= AC_K && t_fit >= 64 &&
+           t_fit <= analog_cell_max_steps(n_features) && t_fit <= sdb_series_argsort_max_steps();
 }
 
 extern "C" int sdb_analog_predict_pruned(int kind, const void* X_train, const void* y_train, const void* X_query,
@@ -1020,11 +1169,14 @@ extern "C" int sdb_analog_predict_pruned(int kind, const void* X_train, const vo
                                          int has_thresh, double thresh, double logistic_c, const int32_t* rand_idx,
                                          void* out, int out_dtype, int64_t ld_out, int32_t* knn_idx,
                                          const uint8_t* cell_valid, int32_t* nonfinite,
-                                         const int32_t* order_train, const int32_t* order_query, int64_t ld_order, void* stream) {
-    if (!order_train || !order_query) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict_pruned: NULL order table");
-    if (dtype != SDB_F32) return sdb_fail(SDB_E_UNSUPPORTED, "sdb_analog_predict_pruned: float32 inputs only (use sdb_analog_predict)");
-    if (ld_order < n_cells) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict_pruned: bad ld_order");
+                                         const int32_t* perm_train, const int32_t* perm_query, const int32_t* box_start,
+                                         const float* bounds, int64_t ld_grid, void* stream) {
+    if (!perm_train || !perm_query || !box_start || !bounds) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict_pruned: NULL grid table");
+    if (ld_grid < n_cells) return sdb_fail(SDB_E_INVALID, "sdb_analog_predict_pruned: bad ld_grid");
+    if (!sdb_analog_pruned_supported(dtype, t_fit, n_features, k))
+        return sdb_fail(SDB_E_UNSUPPORTED, "sdb_analog_predict_pruned: float32, 1..3 predictors, k <= %d, at most %d steps (use sdb_analog_predict)",
+                        AC_K, analog_cell_max_steps(n_features < 1 ? 1 : (n_features > 3 ? 3 : n_features)));
     return analog_predict_impl(kind, X_train, y_train, X_query, dtype, ld, n_cells, t_fit, t_query, n_features, k, has_thresh, thresh,
-                               logistic_c, rand_idx, out, out_dtype, ld_out, knn_idx, cell_valid, nonfinite, order_train, order_query,
-                               ld_order, stream);
+                               logistic_c, rand_idx, out, out_dtype, ld_out, knn_idx, cell_valid, nonfinite,
+                               perm_train, perm_query, box_start, bounds, ld_grid, stream);
 }

@@ -355,9 +355,34 @@ def series_argsort(x: torch.Tensor, row_stride: int, n_steps: int, n_cells: int,
     return order
 
 
+ANALOG_GRID_MIN_STEPS = 2048        # below this the whole window is cheaper to scan than to index
+
+
+def analog_grid_supported(X_train: torch.Tensor, k: int) -> bool:
+    lib = _lib.load()
+    T, p = X_train.shape[0], X_train.shape[1]
+    return (X_train.dtype == torch.float32 and T >= ANALOG_GRID_MIN_STEPS and os.environ.get('SDB_ANALOG_PRUNE', '1') != '0'
+            and bool(lib.sdb_analog_pruned_supported(_lib.SDB_F32, T, p, k)))
+
+
+def analog_grid_fit(X_train: torch.Tensor, valid=None):
+    """The spatial index of every cell's training window (the reference's KDTree build, gard.py:82) →
+    ``(perm_train [T, C], box_start [65, C], bounds [63, C])``."""
+    lib = _lib.load()
+    T, p, C = X_train.shape
+    dev = X_train.device
+    work = torch.empty((T, C), dtype=torch.int32, device=dev)
+    perm = torch.empty((T, C), dtype=torch.int32, device=dev)
+    start = torch.zeros((lib.sdb_analog_grid_boxes() + 1, C), dtype=torch.int32, device=dev)
+    bounds = torch.zeros((lib.sdb_analog_grid_planes(), C), dtype=torch.float32, device=dev)
+    _lib.check(lib.sdb_analog_grid_fit(_ptr(X_train), _code(X_train), C, C, T, p, _ptr(work), _ptr(bounds), _ptr(perm),
+                                       _ptr(start), C, _ptr(valid), _stream()), 'sdb_analog_grid_fit')
+    return perm, start, bounds
+
+
 def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_query: torch.Tensor, k: int, *,
                    thresh=None, rand_idx=None, out_dtype=None, want_idx: bool = False, valid=None,
-                   nonfinite=None, logistic_C: float = 1.0, prune: bool | None = None, order_train=None):
+                   nonfinite=None, logistic_C: float = 1.0, prune: bool | None = None, grid=None):
     """PureAnalog / AnalogRegression fit+predict for all cells (gard.py:58-87, 152-224, 273-364).
 
     X_train [T, p, C], y_train [T, C], X_query [Tq, p, C] → out [Tq, 3, C]."""
@@ -380,22 +405,22 @@ def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_qu
     idx = torch.empty((Tq, k, C), dtype=torch.int32, device=dev) if want_idx else None
     if rand_idx is not None:
         rand_idx = torch.as_tensor(np.ascontiguousarray(rand_idx, dtype=np.int32)).to(dev)
-    # exact pruning needs both windows ordered by the first predictor: float32, at most 32 768 steps, and enough
-    # training rows for the ordered walk to pay for the two argsorts
-    max_steps = lib.sdb_series_argsort_max_steps()
-    can_prune = X_train.dtype == torch.float32 and T <= max_steps and Tq <= max_steps
+    # exact pruning: the training rows and the query steps grouped by the boxes of the quantile grid
+    can_prune = analog_grid_supported(X_train, k)
     if prune is None:
-        prune = can_prune and T >= 2048 and os.environ.get('SDB_ANALOG_PRUNE', '1') != '0'
+        prune = can_prune
     if prune and not can_prune:
-        raise ValueError('pruned analog search needs float32 inputs of at most %d steps' % max_steps)
+        raise ValueError('the pruned analog search covers float32 windows of at least %d steps, 1..3 predictors, k <= 16'
+                         % ANALOG_GRID_MIN_STEPS)
     args = (kind, _ptr(X_train), _ptr(y_train), _ptr(X_query), _code(X_train), C, C, T, Tq, p, k, int(thresh is not None),
             float(thresh) if thresh is not None else 0.0, float(logistic_C), _ptr(rand_idx),
             _ptr(out), _TORCH_CODE[od], C, _ptr(idx), _ptr(valid), _ptr(nonfinite))
     if prune:
-        if order_train is None:
-            order_train = series_argsort(X_train, p * C, T, C, valid)
-        order_query = series_argsort(X_query, p * C, Tq, C, valid)
-        _lib.check(lib.sdb_analog_predict_pruned(*args, _ptr(order_train), _ptr(order_query), C, _stream()),
+        perm_t, start, bounds = grid if grid is not None else analog_grid_fit(X_train, valid)
+        perm_q = torch.empty((Tq, C), dtype=torch.int32, device=dev)
+        _lib.check(lib.sdb_analog_grid_assign(_ptr(X_query), _code(X_query), C, C, Tq, p, _ptr(bounds), _ptr(perm_q), C,
+                                              _ptr(valid), _stream()), 'sdb_analog_grid_assign')
+        _lib.check(lib.sdb_analog_predict_pruned(*args, _ptr(perm_t), _ptr(perm_q), _ptr(start), _ptr(bounds), C, _stream()),
                    'sdb_analog_predict_pruned')
     else:
         _lib.check(lib.sdb_analog_predict(*args, _stream()), 'sdb_analog_predict')

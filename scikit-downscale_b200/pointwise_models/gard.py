@@ -58,14 +58,9 @@ class AnalogBase(RegressorMixin, BaseEstimator):
             raise NotImplementedError(f'n_analogs > {_MAX_ANALOGS} is not supported on the B200 path')
         self._Xtr, self._ytr, self._valid = X.contiguous(), y.contiguous(), valid
         self._nonfinite = torch.zeros(1, dtype=torch.int32, device=X.device)
-        # the counterpart of the reference's KDTree build (gard.py:82): every cell's training rows ordered by the
-        # first predictor, which is what the search prunes on (engine.analog_predict)
-        self._order_train = None
-        lib = _lib.load()
-        if (self._Xtr.dtype == torch.float32 and 2048 <= T <= lib.sdb_series_argsort_max_steps()
-                and os.environ.get('SDB_ANALOG_PRUNE', '1') != '0'):
-            self._order_train = engine.series_argsort(self._Xtr, self._Xtr.shape[1] * self._Xtr.shape[2], T,
-                                                      self._Xtr.shape[2], valid)
+        # the counterpart of the reference's KDTree build (gard.py:82): every cell's training rows grouped by the
+        # boxes of a quantile grid over the first predictors, which is what the search prunes on
+        self._order_train = engine.analog_grid_fit(self._Xtr, valid) if engine.analog_grid_supported(self._Xtr, self.k_) else None
         self.n_features_in_ = X.shape[1]
         return self
 
@@ -91,11 +86,11 @@ class AnalogBase(RegressorMixin, BaseEstimator):
                              f'{self.n_features_in_} features as input.')
         if X.dtype != self._Xtr.dtype:
             X = X.to(self._Xtr.dtype)
-        prune = self._order_train is not None and X.shape[0] <= _lib.load().sdb_series_argsort_max_steps()
+        prune = self._order_train is not None and engine.analog_grid_supported(self._Xtr, k)
         return engine.analog_predict(kind, self._Xtr, self._ytr, X, k, thresh=thresh, rand_idx=rand_idx,
                                      out_dtype=out_dtype, want_idx=want_idx, valid=self._valid,
                                      nonfinite=self._nonfinite, logistic_C=logistic_C, prune=prune,
-                                     order_train=self._order_train if prune else None)
+                                     grid=self._order_train if prune else None)
 
     # ---- per-cell API
     def fit(self, X, y):

@@ -65,7 +65,7 @@ def _both(model_factory, Xtr, ytr, Xq, dev, **kw):
     return res
 
 
-CASES = ['normal', 'const_x0', 'duplicates', 'far_queries', 'clustered', 'p1', 'p4', 'k200']
+CASES = ['normal', 'const_x0', 'duplicates', 'far_queries', 'clustered', 'p1', 'p2', 'k16']
 
 
 @pytest.mark.parametrize('case', CASES)
@@ -73,10 +73,10 @@ def test_pruned_search_equals_brute_force(dev, case):
     p, k, T, Tq, C = 3, 10, 4200, 1500, 5
     if case == 'p1':
         p = 1
-    if case == 'p4':
-        p = 4
-    if case == 'k200':
-        k = 200
+    if case == 'p2':
+        p = 2
+    if case == 'k16':
+        k = 16
     Xtr, ytr, Xq = synth.analog(T, Tq, C, p, seed=7 + len(case))
     rng = np.random.default_rng(3)
     if case == 'const_x0':
@@ -91,7 +91,7 @@ def test_pruned_search_equals_brute_force(dev, case):
     elif case == 'clustered':
         Xtr[:, 0, :] = np.round(Xtr[:, 0, :])          # first predictor on a coarse grid
         Xq[:, 0, :] = np.round(Xq[:, 0, :] * 2) / 2
-    for kind in (['regression'] if case in ('k200', 'p4') else ['regression', 'mean_analogs', 'weight_analogs', 'best_analog']):
+    for kind in (['regression'] if case in ('k16',) else ['regression', 'mean_analogs', 'weight_analogs', 'best_analog']):
         if kind == 'regression':
             mk = lambda: pm().AnalogRegression(n_analogs=k)     # noqa: E731
         else:
@@ -120,7 +120,7 @@ def test_pruned_search_with_thresh_and_masked_cells(dev):
     assert np.isnan(res[1][:, :, 4]).all()
 
 
-@pytest.mark.parametrize('name,T,k', [('PureAnalog', 18250, 10), ('AnalogRegression', 10950, 10), ('AnalogRegression', 10950, 200)])
+@pytest.mark.parametrize('name,T,k', [('PureAnalog', 18250, 10), ('AnalogRegression', 10950, 10), ('AnalogRegression', 10950, 200)])   # k = 200: brute force
 def test_analog_indices_at_baseline_window_lengths(dev, name, T, k):
     """BASELINE configs 4 / 5: 50-year and 30-year daily windows, 3 predictors.  A 4 096-cell block on the device;
     the kNN indices of cells 0, 1, 2047 and 4095 (first / last cell of the block) are compared bit for bit with the
