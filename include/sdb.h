@@ -57,6 +57,7 @@ extern "C" {
 /* group-mean arithmetic (what pandas does in the reference, see oracle/bcsd.py) */
 #define SDB_MEAN_GROUPBY 0   /* df.groupby().mean(): Kahan sum in input dtype   bcsd.py:138,222-223 */
 #define SDB_MEAN_FRAME   1   /* DataFrame.mean(): numpy pairwise sum            groupers.py:84-89   */
+#define SDB_MEAN_NUMPY   2   /* one-column frame .mean(): pairwise over all n    quantile.py:673-674 */
 
 /* PureAnalog kinds (gard.py:310-336) */
 #define SDB_ANALOG_BEST   0

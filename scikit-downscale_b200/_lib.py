@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get('SDB_LIBRARY') or os.path.join(_HERE, 'csrc', 'libsdb.
 
 SDB_F32, SDB_F64 = 0, 1
 MODE_QM, MODE_BCSD_P, MODE_BCSD_T = 0, 1, 2
-MEAN_GROUPBY, MEAN_FRAME = 0, 1
+MEAN_GROUPBY, MEAN_FRAME, MEAN_NUMPY = 0, 1, 2
 EXTRAPOLATE = {None: 0, '1to1': 0, 'min': 1, 'max': 2, 'both': 3}    # SDB_EXTRAPOLATE_* (include/sdb.h)
 
 

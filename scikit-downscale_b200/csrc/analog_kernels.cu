@@ -341,15 +341,16 @@ __device__ void regression_epilogue(const AnalogParams& a, int q, int64_t c, int
     }
     double beta[P];
     bool solved = false;
-    if constexpr (LOGIT) {
-        // few analogs above the threshold: rank-deficient centred cloud → the minimum-norm solution
-        // (only compiled into the threshold kernels; without a threshold m = k > p in practice)
-        if (m <= p) { sym_minnorm_solve<P>(A, b, p, beta); solved = true; }
-    }
+    // no more regression samples than predictors: rank-deficient centred cloud → the minimum-norm solution
+    // (what scipy's gelsd under sklearn's LinearRegression returns)
+    if (m <= p) { sym_minnorm_solve<P>(A, b, p, beta); solved = true; }
     if (!solved) {
-        // Cholesky A = L L^T (lower, in place); a zero pivot (degenerate analog cloud) drops that
-        // direction, i.e. a minimum-norm-like solution with beta_f = 0.
+        // Cholesky A = L L^T.  A pivot that is zero up to roundoff RELATIVE to its diagonal entry (collinear or
+        // duplicated analog rows) means the cloud is rank deficient: minimum-norm solution instead of huge
+        // coefficients; an exactly constant predictor (zero diagonal) just drops out.
         bool live[P];
+        bool deficient = false;
+        double L[P][P];
 #pragma unroll
         for (int f = 0; f < P; ++f) {
             live[f] = f < p;
@@ -357,28 +358,32 @@ __device__ void regression_epilogue(const AnalogParams& a, int q, int64_t c, int
             for (int g = 0; g <= f; ++g) {
                 double s = A[f][g];
 #pragma unroll
-                for (int h = 0; h < g; ++h) s -= A[f][h] * A[g][h];
+                for (int h = 0; h < g; ++h) s -= L[f][h] * L[g][h];
                 if (g == f) {
-                    if (!(s > 1e-300) || !live[f]) { live[f] = false; A[f][f] = 1.0; }
-                    else A[f][f] = sqrt(s);
+                    if (live[f] && A[f][f] > 0.0 && !(s > 1e-13 * A[f][f])) deficient = true;
+                    if (!(s > 1e-300) || !live[f]) { live[f] = false; L[f][f] = 1.0; }
+                    else L[f][f] = sqrt(s);
                 } else {
-                    A[f][g] = live[g] ? s / A[g][g] : 0.0;
+                    L[f][g] = live[g] ? s / L[g][g] : 0.0;
                 }
             }
         }
+        if (deficient) { sym_minnorm_solve<P>(A, b, p, beta); solved = true; }
+        if (!solved) {
 #pragma unroll
         for (int f = 0; f < P; ++f) {                      // forward substitution
             double s = b[f];
 #pragma unroll
-            for (int h = 0; h < f; ++h) s -= A[f][h] * beta[h];
-            beta[f] = live[f] ? s / A[f][f] : 0.0;
+            for (int h = 0; h < f; ++h) s -= L[f][h] * beta[h];
+            beta[f] = live[f] ? s / L[f][f] : 0.0;
         }
 #pragma unroll
         for (int f = P - 1; f >= 0; --f) {                 // back substitution
             double s = beta[f];
 #pragma unroll
-            for (int h = f + 1; h < P; ++h) s -= A[h][f] * beta[h];
-            beta[f] = live[f] ? s / A[f][f] : 0.0;
+            for (int h = f + 1; h < P; ++h) s -= L[h][f] * beta[h];
+            beta[f] = live[f] ? s / L[f][f] : 0.0;
+        }
         }
     }
     double icpt = ym;

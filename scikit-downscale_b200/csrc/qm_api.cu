@@ -37,6 +37,11 @@ __global__ void group_mean_kernel(const T* __restrict__ v, int64_t ld, int64_t C
         }
         flag_nonfinite(s, nonfinite);
         *dst = s / (T)n;
+    } else if (how == SDB_MEAN_NUMPY) {
+        // contiguous 1-D ndarray.sum in the input dtype: pairwise over all n (a one-column DataFrame.mean())
+        const T s = np_pairwise<T>(a, 0, n);
+        flag_nonfinite(s, nonfinite);
+        *dst = s / (T)n;
     } else {
         // ndarray.sum: first element copied as the initial value, pairwise over the rest
         T s = a(0);
@@ -69,7 +74,7 @@ extern "C" int sdb_group_mean(const void* v, int dtype, int64_t ld, int64_t n_ce
     if (!v || !rows || !len || !climo) return sdb_fail(SDB_E_INVALID, "sdb_group_mean: NULL pointer");
     if (n_cells <= 0 || n_groups <= 0 || max_len <= 0 || ld < n_cells || ld_out < n_cells)
         return sdb_fail(SDB_E_INVALID, "sdb_group_mean: bad shape");
-    if (how != SDB_MEAN_GROUPBY && how != SDB_MEAN_FRAME) return sdb_fail(SDB_E_INVALID, "sdb_group_mean: bad how");
+    if (how != SDB_MEAN_GROUPBY && how != SDB_MEAN_FRAME && how != SDB_MEAN_NUMPY) return sdb_fail(SDB_E_INVALID, "sdb_group_mean: bad how");
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)((n_cells + 127) / 128), (unsigned)n_groups);
     if (dtype == SDB_F32)

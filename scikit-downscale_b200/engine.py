@@ -37,6 +37,35 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device_of_first_tensor(fn):
+    """Run an engine entry point with the device of its first CUDA tensor argument current (kernel launches and the
+    stream handed to the C ABI then belong to that device — not to whatever device the caller had selected) and
+    check that every CUDA tensor argument lives on that one device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        stack = list(args) + list(kwargs.values())
+        while stack:
+            v = stack.pop()
+            if isinstance(v, torch.Tensor):
+                if v.is_cuda:
+                    if dev is None:
+                        dev = v.device
+                    elif v.device != dev:
+                        raise RuntimeError(f'{fn.__name__}: operands on different devices ({dev} and {v.device})')
+            elif isinstance(v, QMFitted):
+                stack.extend(t for t in (v.sorted_state, v.x_climo, v.y_climo, v.valid) if t is not None)
+            elif isinstance(v, (tuple, list)):
+                stack.extend(v)
+        if dev is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return wrapped
+
+
 def _check_2d(t: torch.Tensor, name: str) -> int:
     if not t.is_cuda:
         raise RuntimeError(f'{name} must be a CUDA tensor (skdownscale_b200 has no CPU path)')
@@ -128,6 +157,7 @@ def cell_mask(first_row: torch.Tensor) -> torch.Tensor:
     return (~torch.isnan(first_row)).to(torch.uint8).contiguous()
 
 
+@_on_device_of_first_tensor
 def group_mean(v: torch.Tensor, table: GroupTable, how: int, valid=None, nonfinite=None, out=None) -> torch.Tensor:
     lib = _lib.load()
     ld = _check_2d(v, 'v')
@@ -159,6 +189,7 @@ def copy2d(dst: torch.Tensor, src: torch.Tensor, to_device, stream=None) -> None
                                       stream if stream is not None else _stream()), 'sdb_memcpy2d_async')
 
 
+@_on_device_of_first_tensor
 def peer_copy2d(dst: torch.Tensor, src: torch.Tensor, stream=None, n_ctas: int = 32, method: str = 'kernel') -> None:
     """Push a [rows, cols] block into (possibly peer) device memory: ``method='kernel'`` = ``sdb_peer_copy2d``
     (SM loads / stores over NVLink; needs 16-byte aligned rows, else falls back), ``'ce'`` = ``cudaMemcpy2DAsync``."""
@@ -200,6 +231,7 @@ def alloc_state(dtype, n_cells: int, device, sort_table: GroupTable, mean_table:
                     nonfinite=torch.zeros(1, dtype=torch.int32, device=device))
 
 
+@_on_device_of_first_tensor
 def qm_fit_into(st: QMFitted, y: torch.Tensor, X: torch.Tensor | None = None,
                 mean_how: int = _lib.MEAN_GROUPBY) -> QMFitted:
     """Run the fit kernels for the cells of ``st`` (a whole state or a :meth:`QMFitted.cells` view)."""
@@ -221,6 +253,7 @@ def qm_fit_into(st: QMFitted, y: torch.Tensor, X: torch.Tensor | None = None,
     return st
 
 
+@_on_device_of_first_tensor
 def qm_fit(y: torch.Tensor, sort_table: GroupTable, *, valid=None, X=None, mean_table=None,
            mean_how: int = _lib.MEAN_GROUPBY, want_y_climo: bool = True) -> QMFitted:
     """fit: sort every (cell, group) of ``y`` and compute the climatologies.
@@ -242,6 +275,7 @@ def fused_supported(dtype, table: GroupTable) -> bool:
     return dtype == torch.float32 and 0 < table.max_len <= FUSED_MAX_LEN
 
 
+@_on_device_of_first_tensor
 def qm_fit_predict(y: torch.Tensor, X_pred: torch.Tensor, table: GroupTable, mode: int, *, X_train=None,
                    return_anoms: bool = False, valid=None, out=None, keep_state: bool = True, stats=None):
     """fit + predict in one pass when both share the time index (``sdb_bcsd_fit_predict``): the sorted
@@ -288,6 +322,7 @@ def qm_fit_predict(y: torch.Tensor, X_pred: torch.Tensor, table: GroupTable, mod
     return out, st
 
 
+@_on_device_of_first_tensor
 def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, return_anoms: bool = False,
                roll_nbr: np.ndarray | None = None, out_dtype=None, want_rank: bool = False, out=None,
                climo_gid: np.ndarray | None = None, cunnane=None):
@@ -346,6 +381,7 @@ def qm_predict(st: QMFitted, X: torch.Tensor, table: GroupTable, mode: int, *, r
     return (out, rank) if want_rank else out
 
 
+@_on_device_of_first_tensor
 def series_argsort(x: torch.Tensor, row_stride: int, n_steps: int, n_cells: int, valid=None) -> torch.Tensor:
     """Per cell, the time steps in ascending order of ``x[t * row_stride + c]`` → int32 ``[n_steps, n_cells]``."""
     lib = _lib.load()
@@ -365,6 +401,7 @@ def analog_grid_supported(X_train: torch.Tensor, k: int) -> bool:
             and bool(lib.sdb_analog_pruned_supported(_lib.SDB_F32, T, p, k)))
 
 
+@_on_device_of_first_tensor
 def analog_grid_fit(X_train: torch.Tensor, valid=None):
     """The spatial index of every cell's training window (the reference's KDTree build, gard.py:82) →
     ``(perm_train [T, C], box_start [65, C], bounds [63, C])``."""
@@ -380,6 +417,7 @@ def analog_grid_fit(X_train: torch.Tensor, valid=None):
     return perm, start, bounds
 
 
+@_on_device_of_first_tensor
 def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_query: torch.Tensor, k: int, *,
                    thresh=None, rand_idx=None, out_dtype=None, want_idx: bool = False, valid=None,
                    nonfinite=None, logistic_C: float = 1.0, prune: bool | None = None, grid=None):
@@ -430,6 +468,7 @@ def analog_predict(kind: int, X_train: torch.Tensor, y_train: torch.Tensor, X_qu
 # ---------------------------------------------------------------------------------------------
 # CDF-to-CDF regressors (QuantileMappingReressor / EquidistantCdfMatcher, quantile.py:160-395, 556-636)
 # ---------------------------------------------------------------------------------------------
+@_on_device_of_first_tensor
 def series_rank(X: torch.Tensor, table: GroupTable, *, ordinal: bool, valid=None, nonfinite=None) -> torch.Tensor:
     """1-based rank of every value inside its (cell, group) series → int32 ``[T, C]``."""
     lib = _lib.load()
@@ -445,6 +484,7 @@ def series_rank(X: torch.Tensor, table: GroupTable, *, ordinal: bool, valid=None
     return rank
 
 
+@_on_device_of_first_tensor
 def qmr_frame(sx: QMFitted, sy: QMFitted, extrapolate: int, n_endpoints: int) -> torch.Tensor:
     """Synthetic frame points of the fitted X / y CDFs of every cell → float64 ``[C, 4]``."""
     lib = _lib.load()
@@ -456,6 +496,7 @@ def qmr_frame(sx: QMFitted, sy: QMFitted, extrapolate: int, n_endpoints: int) ->
     return frame
 
 
+@_on_device_of_first_tensor
 def qmr_predict(kind: int, X: torch.Tensor, sx: QMFitted, sy: QMFitted, frame: torch.Tensor, extrapolate: int,
                 one_to_one: bool, rank: torch.Tensor | None = None) -> torch.Tensor:
     lib = _lib.load()
@@ -476,6 +517,7 @@ def qmr_predict(kind: int, X: torch.Tensor, sx: QMFitted, sy: QMFitted, frame: t
 # ---------------------------------------------------------------------------------------------
 # Detrending quantile map (QuantileMapper(detrend=True), quantile.py:94-98, 127-145)
 # ---------------------------------------------------------------------------------------------
+@_on_device_of_first_tensor
 def group_trend(v: torch.Tensor, table: GroupTable, valid=None, nonfinite=None):
     """LinearTrendTransformer.fit of every (cell, group) → (slope, intercept) float64 ``[G, C]``."""
     lib = _lib.load()
@@ -490,6 +532,7 @@ def group_trend(v: torch.Tensor, table: GroupTable, valid=None, nonfinite=None):
     return slope, icpt
 
 
+@_on_device_of_first_tensor
 def trend_apply(mode: int, v: torch.Tensor, table: GroupTable, slope, icpt, icpt_ref=None, valid=None) -> torch.Tensor:
     """Remove (``_lib.TREND_REMOVE``) or restore (``_lib.TREND_RESTORE``) the group trend lines → float64."""
     lib = _lib.load()
@@ -520,6 +563,7 @@ def _climo_by_sort(st: QMFitted, device):
     return x_climo, y_climo
 
 
+@_on_device_of_first_tensor
 def qm_predict_detrended(st_raw: QMFitted, st_res: QMFitted, icpt_fit: torch.Tensor, X: torch.Tensor, table: GroupTable,
                          mode: int, *, return_anoms: bool = False, roll_nbr=None, out_dtype=None, cunnane=None):
     """predict with detrending mappers: (shift →) remove the new data's trend → map the residuals through
@@ -529,6 +573,14 @@ def qm_predict_detrended(st_raw: QMFitted, st_res: QMFitted, icpt_fit: torch.Ten
     lib = _lib.load()
     ld = _check_2d(X, 'X')
     T, C = X.shape
+    if C != st_raw.n_cells:
+        raise ValueError(f'X has {C} cells, the model was fitted on {st_raw.n_cells}')
+    raw_dtype = st_res.extra.get('raw_dtype', st_raw.dtype)
+    if X.dtype != raw_dtype:
+        # sdb_bcsd_shift reads x_climo in X's element type: a float64 X against float32 climatologies would read
+        # out of bounds.  The reference accepts a predict dtype that differs from fit's — cast like predict() does.
+        X = X.to(raw_dtype)
+        ld = _check_2d(X, 'X')
     dev = X.device
     rows, length = table.device(dev)
     gid = _fit_gids(st_res, table, dev)
@@ -561,6 +613,7 @@ def qm_predict_detrended(st_raw: QMFitted, st_res: QMFitted, icpt_fit: torch.Ten
 # ---------------------------------------------------------------------------------------------
 # PureRegression (gard.py:367-504)
 # ---------------------------------------------------------------------------------------------
+@_on_device_of_first_tensor
 def pure_regression_fit(X_train: torch.Tensor, y_train: torch.Tensor, *, thresh=None, logistic_C: float = 1.0,
                         valid=None, nonfinite=None) -> torch.Tensor:
     """One OLS (+ logistic exceedance model) per cell → model ``[C, model_ld]`` float64 (library-private layout)."""
@@ -577,6 +630,7 @@ def pure_regression_fit(X_train: torch.Tensor, y_train: torch.Tensor, *, thresh=
     return model
 
 
+@_on_device_of_first_tensor
 def pure_regression_predict(model: torch.Tensor, X_query: torch.Tensor, *, out_dtype=None, valid=None,
                             nonfinite=None) -> torch.Tensor:
     lib = _lib.load()

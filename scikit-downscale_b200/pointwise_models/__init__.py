@@ -1,14 +1,16 @@
 """Drop-in surface of ``skdownscale.pointwise_models`` for the B200 hot path
 (skdownscale/pointwise_models/__init__.py:1-36).  Estimators outside the hot path
 (ZScoreRegressor, GroupedRegressor, ...) are not provided; QuantileMappingReressor and
-EquidistantCdfMatcher are the first "next" row of SURVEY.md §8(f).
+EquidistantCdfMatcher are the first "next" row of SURVEY.md §8(f), LinearTrendTransformer and
+TrendAwareQuantileMappingRegressor the second.
 """
 
 from .bcsd import BcsdPrecipitation, BcsdTemperature
 from .core import PointWiseDownscaler
 from .gard import AnalogRegression, PureAnalog, PureRegression
 from .groupers import DAY_GROUPER, MONTH_GROUPER, PaddedDOYGrouper
-from .quantile import EquidistantCdfMatcher, QuantileMapper, QuantileMappingReressor
+from .quantile import (EquidistantCdfMatcher, LinearTrendTransformer, QuantileMapper, QuantileMappingReressor,
+                       TrendAwareQuantileMappingRegressor)
 
 __all__ = [
     'BcsdPrecipitation',
@@ -23,4 +25,6 @@ __all__ = [
     'QuantileMapper',
     'QuantileMappingReressor',
     'EquidistantCdfMatcher',
+    'LinearTrendTransformer',
+    'TrendAwareQuantileMappingRegressor',
 ]

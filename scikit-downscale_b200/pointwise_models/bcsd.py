@@ -145,6 +145,8 @@ class BcsdBase(TimeSynchronousDownscaler):
             # different shape and the reference raises
             raise ValueError('shape of climo is not equal to input array')
         table, nbr = self._predict_tables(index)
+        if X.dtype != self._state.dtype:
+            X = X.to(self._state.dtype)          # fit float32 / predict float64 works like the reference (core.py:254)
         if getattr(self, '_detrend', False):
             if want_rank:
                 raise NotImplementedError('rank instrumentation is not available with detrend=True')

@@ -16,6 +16,8 @@ Only estimators of this package run (there is no generic per-cell Python fallbac
 
 from __future__ import annotations
 
+import copy
+
 import numpy as np
 import pandas as pd
 import torch
@@ -139,7 +141,9 @@ class PointWiseDownscaler:
             raise TypeError(f'unsupported fit parameters on the B200 path: {sorted(kws)}')
         dev = self._dev()
         bx = self._to_block(X, fd, time)
-        model = self._model
+        # core.py:87: the reference fits deep copies, the estimator handed to the wrapper is never fitted itself —
+        # two wrappers sharing one estimator (or a refit on another block) must not overwrite each other's state
+        model = copy.deepcopy(self._model)
         if self._streamed(bx) and args:
             by = self._to_block_y(args[0], fd, time)
             if bx.index is None:

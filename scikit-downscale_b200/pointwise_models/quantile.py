@@ -7,6 +7,8 @@ quantile.py:420-432) travel to the kernels as ``sdb_cunnane_opts``.
 
 from __future__ import annotations
 
+import copy
+
 import numpy as np
 import torch
 from sklearn.base import BaseEstimator, RegressorMixin, TransformerMixin
@@ -96,6 +98,9 @@ class QuantileMapper(TransformerMixin, BaseEstimator):
     def transform_batched(self, X: torch.Tensor, out_dtype=None, want_rank=False):
         if not hasattr(self, '_state'):
             raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet.")
+        fit_dtype = self._state.extra.get('raw_dtype', self._state.dtype)
+        if X.dtype != fit_dtype:
+            X = X.to(fit_dtype)                    # the reference accepts a transform dtype that differs from fit's
         if self.detrend:
             if want_rank:
                 raise NotImplementedError('rank instrumentation is not available with detrend=True')
@@ -231,3 +236,146 @@ class EquidistantCdfMatcher(QuantileMappingReressor):
         # np.argsort position of every step inside its cell's series (quantile.py:607-609)
         return engine.series_rank(X, whole_series_table(X.shape[0]), ordinal=True, valid=self._sx.valid,
                                   nonfinite=self._sx.nonfinite)
+
+
+
+class LinearTrendTransformer(TransformerMixin, BaseEstimator):
+    """Transform features by removing linear trends (trend.py:14-91): the least-squares line of every series on
+    ``arange(n)`` (``sdb_group_trend``), subtracted / added back by ``sdb_trend_apply``.  ``transform`` /
+    ``inverse_transform`` / ``trendline`` evaluate the FITTED line at positions ``0 .. len(X) - 1`` of the array
+    they are given, like the reference.  Results are float64 (the reference's ``X - lr_model_.predict(...)``)."""
+
+    def __init__(self, lr_kwargs=None):
+        self.lr_kwargs = lr_kwargs
+
+    # ---- batched (all cells): X [T, C] CUDA tensor
+    def fit_batched(self, X: torch.Tensor, valid=None):
+        check_lt_kwargs({'lr_kwargs': self.lr_kwargs})
+        self._flag = torch.zeros(1, dtype=torch.int32, device=X.device)
+        self._slope, self._icpt = engine.group_trend(X, whole_series_table(X.shape[0]), valid, self._flag)
+        self._valid = valid
+        return self
+
+    def _require_fit(self):
+        if not hasattr(self, '_slope'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
+                                 "appropriate arguments before using this estimator.")
+
+    def transform_batched(self, X: torch.Tensor) -> torch.Tensor:
+        self._require_fit()
+        return engine.trend_apply(_lib.TREND_REMOVE, X, whole_series_table(X.shape[0]), self._slope, self._icpt, valid=self._valid)
+
+    def inverse_transform_batched(self, X: torch.Tensor) -> torch.Tensor:
+        self._require_fit()
+        # RESTORE = (v + line) - (intercept - intercept_ref): intercept_ref = intercept leaves v + line
+        return engine.trend_apply(_lib.TREND_RESTORE, X, whole_series_table(X.shape[0]), self._slope, self._icpt, self._icpt,
+                                  valid=self._valid)
+
+    def trendline_batched(self, n: int) -> torch.Tensor:
+        self._require_fit()
+        zeros = torch.zeros((n, self._slope.shape[1]), dtype=torch.float64, device=self._slope.device)
+        return self.inverse_transform_batched(zeros)
+
+    def check_fit(self):
+        if int(self._flag.item()) != 0:
+            self._flag.zero_()
+            raise ValueError('Input contains NaN or infinity.')
+
+    # ---- per-cell API of the reference: X [n, n_features] array-like
+    def fit(self, X, y=None):
+        x, _, _ = series_to_device(X, cuda_device())
+        self.fit_batched(x)               # every column is a series of its own (multi-output LinearRegression)
+        self.check_fit()
+        self.lr_model_ = True
+        self.n_features_in_ = x.shape[1]
+        return self
+
+    def _columns(self, X):
+        x, _, _ = series_to_device(X, cuda_device())
+        self._require_fit()
+        if x.shape[1] != self._slope.shape[1]:
+            raise ValueError(f'X has {x.shape[1]} features, but LinearTrendTransformer is expecting {self._slope.shape[1]} features as input.')
+        return x
+
+    def transform(self, X):
+        return self.transform_batched(self._columns(X)).cpu().numpy()
+
+    def inverse_transform(self, X):
+        return self.inverse_transform_batched(self._columns(X)).cpu().numpy()
+
+    def trendline(self, X):
+        return self.trendline_batched(self._columns(X).shape[0]).cpu().numpy()
+
+
+class TrendAwareQuantileMappingRegressor(RegressorMixin, BaseEstimator):
+    """Experimental meta estimator for trend-aware quantile mapping (quantile.py:639-716): the CDF-to-CDF regressor
+    is fitted on linearly detrended X and y; predict maps the detrended new X and adds back the new trend line
+    (centred at zero) plus ``(mean(X_new) - mean(X_fit)) + mean(y_fit)``.  Like the reference, only the default
+    ``LinearTrendTransformer()`` exists (passing another one leaves the attribute unset there, quantile.py:655-656)."""
+
+    def __init__(self, qm_estimator=None, trend_transformer=None):
+        self.qm_estimator = qm_estimator
+        if trend_transformer is None:
+            self.trend_transformer = LinearTrendTransformer()
+
+    def _check(self):
+        if not isinstance(self.qm_estimator, QuantileMappingReressor):
+            raise TypeError('qm_estimator must be a QuantileMappingReressor / EquidistantCdfMatcher of this package; '
+                            'there is no per-cell Python fallback on the B200 path')
+        if not hasattr(self, 'trend_transformer'):
+            raise AttributeError("'TrendAwareQuantileMappingRegressor' object has no attribute 'trend_transformer'")
+
+    # ---- batched (all cells): X, y [T, C] CUDA tensors
+    def fit_batched(self, X: torch.Tensor, y: torch.Tensor, valid=None):
+        self._check()
+        table = whole_series_table(X.shape[0])
+        flag = torch.zeros(1, dtype=torch.int32, device=X.device)
+        self._x_mean_fit = engine.group_mean(X, table, _lib.MEAN_NUMPY, valid, flag)            # [1, C], input dtype
+        self._y_mean_fit = engine.group_mean(y, whole_series_table(y.shape[0]), _lib.MEAN_NUMPY, valid, flag)
+        x_res = copy.deepcopy(self.trend_transformer).fit_batched(X, valid).transform_batched(X)
+        y_res = copy.deepcopy(self.trend_transformer).fit_batched(y, valid).transform_batched(y)
+        self.qm_estimator.fit_batched(x_res, y_res, valid=valid)
+        self._valid, self._flag = valid, flag
+        return self
+
+    def check_fit(self):
+        self.qm_estimator.check_fit()
+        if int(self._flag.item()) != 0:
+            self._flag.zero_()
+            raise ValueError('Input contains NaN or infinity.')
+
+    def predict_batched(self, X: torch.Tensor) -> torch.Tensor:
+        if not hasattr(self, '_x_mean_fit'):
+            raise NotFittedError(f"This {type(self).__name__} instance is not fitted yet. Call 'fit' with "
+                                 "appropriate arguments before using this estimator.")
+        n = X.shape[0]
+        table = whole_series_table(n)
+        lt = copy.deepcopy(self.trend_transformer).fit_batched(X, self._valid)
+        y_hat = self.qm_estimator.predict_batched(lt.transform_batched(X))                      # float64 [n, C]
+        x_mean = engine.group_mean(X, table, _lib.MEAN_NUMPY, self._valid, self._flag)
+        delta = ((x_mean - self._x_mean_fit.to(x_mean.dtype)) + self._y_mean_fit.to(x_mean.dtype)).to(torch.float64)
+        line_mean = lt._slope * ((n - 1) / 2.0) + lt._icpt                                       # mean of the new trend line
+        # y_hat + (line - mean(line)) + delta, in one pass: RESTORE adds the line and moves its intercept
+        return engine.trend_apply(_lib.TREND_RESTORE, y_hat, table, lt._slope, lt._icpt, lt._icpt - line_mean + delta,
+                                  valid=self._valid)
+
+    # ---- per-cell API of the reference (one series)
+    def fit(self, X, y):
+        dev = cuda_device()
+        x, _, _ = series_to_device(X, dev)
+        yt, _, _ = series_to_device(y, dev)
+        if x.shape[1] != 1 or yt.shape[1] != 1:
+            raise ValueError('X and y must be single-column')
+        if x.dtype != yt.dtype:
+            x, yt = x.to(torch.float64), yt.to(torch.float64)
+        self.fit_batched(x, yt)
+        self.check_fit()
+        return self
+
+    def predict(self, X):
+        x, _, _ = series_to_device(X, cuda_device())
+        if hasattr(self, '_x_mean_fit') and x.dtype != self._x_mean_fit.dtype:
+            x = x.to(self._x_mean_fit.dtype)
+        out = self.predict_batched(x[:, :1].contiguous())
+        self.check_fit()
+        return out.cpu().numpy().reshape(-1, 1)

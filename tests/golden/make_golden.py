@@ -258,6 +258,7 @@ def main():
 
     bcsd_p_case('bcsd_p_month_detrend', 1461, 1461, 2, 32, qm_kwargs={'detrend': True})
     bcsd_p_case('bcsd_p_month_anoms', 1461, 1461, 3, 30)
+    bcsd_p_case('bcsd_p_month_30yr', 10950, 10950, 2, 33)                  # BASELINE config 3's series length
     bcsd_p_case('bcsd_p_month_abs_future', 1096, 1461, 3, 31, start_pred='1984-01-01', return_anoms=False)
     bcsd_p_case('bcsd_p_nasanex', 1096, 1096, 2, 32, start_fit='1980-01-01',
                 time_grouper='daily_nasa-nex', return_anoms=False)
@@ -303,6 +304,7 @@ def main():
 
     ar_case('analogreg_k10', 300, 120, 2, 50, 10)
     ar_case('analogreg_k200', 400, 40, 1, 51, 200)
+    ar_case('analogreg_k10_30yr', 10950, 160, 2, 52, 10)                   # BASELINE config 5's training window
 
     # AnalogRegression(thresh=...) (gard.py:201-215).  Query steps whose analogs are ALL at or below the
     # threshold make the reference raise, so they are dropped from the query set (the error path has

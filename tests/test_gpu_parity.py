@@ -218,6 +218,46 @@ def test_qm_regressor_and_edcdf_golden(dev, golden, name, ex):
     assert_close(o[ok], g[f'qmr_{tag}'][ok, 0], scale=scale)
 
 
+@pytest.mark.parametrize('name', ['trend_aware_qmr', 'trend_aware_qmr_f64'])
+def test_trend_aware_qm_regressor_golden(dev, golden, name):
+    """TrendAwareQuantileMappingRegressor (quantile.py:639-716) against the live-reference vectors, batched over the
+    cells and through the per-cell API."""
+    g = golden(name)
+    for ex, key in ((None, 'out_none'), ('1to1', 'out_1to1')):
+        m = pm().TrendAwareQuantileMappingRegressor(pm().QuantileMappingReressor(extrapolate=ex, n_endpoints=6))
+        m.fit_batched(eng().as_device(g['Xtr'], dev), eng().as_device(g['ytr'], dev))
+        m.check_fit()
+        out = m.predict_batched(eng().as_device(g['Xp'], dev)).cpu().numpy()
+        assert out.dtype == np.float64
+        np.testing.assert_allclose(out, g[key], rtol=1e-9, atol=1e-9)
+        m1 = pm().TrendAwareQuantileMappingRegressor(pm().QuantileMappingReressor(extrapolate=ex, n_endpoints=6))
+        o1 = m1.fit(g['Xtr'][:, :1], g['ytr'][:, :1]).predict(g['Xp'][:, :1])
+        assert o1.shape == (g['Xp'].shape[0], 1)
+        np.testing.assert_allclose(o1[:, 0], g[key][:, 0], rtol=1e-9, atol=1e-9)
+
+
+def test_linear_trend_transformer_roundtrip(dev):
+    """The reference's own known-answer test (test_pointwise_models.py:56-78): a pure line detrends to zero with the
+    fitted slope / intercept, inverse_transform restores the data; plus the oracle's line on noisy columns."""
+    n = 100
+    trend, yint = 1.5, 3.0
+    X = (np.arange(n) * trend + yint).reshape(-1, 1)
+    lt = pm().LinearTrendTransformer().fit(X)
+    np.testing.assert_allclose(lt._slope.cpu().numpy().ravel(), [trend], rtol=1e-12)
+    np.testing.assert_allclose(lt._icpt.cpu().numpy().ravel(), [yint], rtol=1e-10)
+    Xt = lt.transform(X)
+    np.testing.assert_allclose(Xt, np.zeros((n, 1)), atol=1e-10)
+    np.testing.assert_allclose(lt.inverse_transform(Xt), X, rtol=1e-12, atol=1e-10)
+    rng = np.random.default_rng(4)
+    A = (rng.standard_normal((257, 3)) + np.linspace(0, 3, 257)[:, None]).astype(np.float32)
+    lt = pm().LinearTrendTransformer().fit(A)
+    line = lt.trendline(A)
+    for c in range(3):
+        slope, icpt = oracle.linear_trend_fit(A[:, c])
+        np.testing.assert_allclose(line[:, c], np.arange(257) * slope + icpt, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(lt.transform(A), A.astype(np.float64) - line, rtol=0, atol=1e-12)
+
+
 def test_edcdf_known_answer(dev, golden):
     """The reference's own exact test (test_pointwise_models.py:323-344)."""
     x = golden('edcdf_known_answer')['x']
@@ -278,6 +318,7 @@ def test_bcsd_temperature_golden(dev, golden, name, kw):
 
 @pytest.mark.parametrize('name,kw', [
     ('bcsd_p_month_anoms', {}),
+    ('bcsd_p_month_30yr', {}),
     ('bcsd_p_month_detrend', {'qm_kwargs': {'detrend': True}}),
     ('bcsd_p_month_abs_future', {'return_anoms': False}),
     ('bcsd_p_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
@@ -492,7 +533,7 @@ def test_full_shard_headline_and_precipitation(dev):
     boundaries and at random are compared with the oracle (1e-5), which exercises the full-size launch
     geometry and 64-bit addressing; (b) the per-month quantile map of X onto y's distribution
     (BcsdPrecipitation, return_anoms=False) — for two whole months EVERY cell must equal the fitted
-    order statistic at its tie-max rank (exact, computed independently with torch)."""
+    order statistic at its tie-max rank (exact, computed independently with torch), on ZERO-INFLATED fields."""
     if torch.cuda.get_device_properties(dev).total_memory < 60e9:
         pytest.skip('needs ~35 GB of device memory')
     T, C = 10950, 129600
@@ -518,15 +559,27 @@ def test_full_shard_headline_and_precipitation(dev):
         st = oracle.bcsd_temperature_fit(xs[:, k], ys[:, k], groups)
         o = oracle.bcsd_temperature_predict(st, ps[:, k], groups, groups, True)
         assert_close(got[:, k], o.astype(np.float32), scale=np.std(ys[:, k]))
-    del out, m
+    del out, m, Xtr, ytr, Xp
     torch.cuda.empty_cache()
+    # (b) ZERO-INFLATED gamma fields (Gamma(.8, 6) where U >= p_dry, else 0): the zeros of a month
+    # are one exact-tie run of hundreds that takes the run's highest rank — the register tie-run path of the tile
+    # kernels at the full launch geometry
+    def precip(p_dry):
+        x = torch._standard_gamma(torch.full((T, C), 0.8, device=dev, dtype=torch.float32)).mul_(6.0)
+        x[torch.rand((T, C), device=dev, generator=gen) < p_dry] = 0.0
+        return x
+
+    ytr, Xp = precip(0.5), precip(0.55)
     q = pm().BcsdPrecipitation(return_anoms=False)
-    q.fit_batched(Xtr, ytr, idx)
+    q.fit_batched(ytr, ytr, idx)
     out = q.predict_batched(Xp, idx)
+    q._state.check_finite()
     month = torch.as_tensor(np.asarray(idx.month), device=dev)
     for mo in (2, 8):
         sel = month == mo
         torch.testing.assert_close(out[sel], _expected_rank_map(Xp[sel], ytr[sel]), rtol=0, atol=0)
+    frac_zero = float((Xp == 0).float().mean())
+    assert 0.5 < frac_zero < 0.6
 
 
 # ------------------------------------------------------------------ GARD
@@ -551,7 +604,7 @@ def test_pure_analog_k200_golden(dev, golden):
     assert_close(pw.predict(g['Xq']), g['out'], scale=np.std(g['ytr']))
 
 
-@pytest.mark.parametrize('name,k', [('analogreg_k10', 10), ('analogreg_k200', 200)])
+@pytest.mark.parametrize('name,k', [('analogreg_k10', 10), ('analogreg_k200', 200), ('analogreg_k10_30yr', 10)])
 def test_analog_regression_golden(dev, golden, name, k):
     g = golden(name)
     pw = pm().PointWiseDownscaler(pm().AnalogRegression(n_analogs=k))

@@ -112,6 +112,7 @@ def test_bcsd_temperature(golden, name, kw):
 
 @pytest.mark.parametrize('name,kw', [
     ('bcsd_p_month_anoms', {}),
+    ('bcsd_p_month_30yr', {}),
     ('bcsd_p_month_detrend', {'detrend': True}),
     ('bcsd_p_month_abs_future', {'return_anoms': False}),
     ('bcsd_p_nasanex', {'time_grouper': 'daily_nasa-nex', 'return_anoms': False}),
@@ -161,7 +162,7 @@ def test_pure_analog_k200(golden):
     _close(o.astype(np.float32), g['out'][:, :, 0], rtol=2e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize('name,k', [('analogreg_k10', 10), ('analogreg_k200', 200)])
+@pytest.mark.parametrize('name,k', [('analogreg_k10', 10), ('analogreg_k200', 200), ('analogreg_k10_30yr', 10)])
 def test_analog_regression(golden, name, k):
     g = golden(name)
     for c in range(g['Xq'].shape[-1]):
