@@ -222,6 +222,18 @@ qm_fit_long_kernel(const float* __restrict__ y, int64_t ld, int64_t C,
                 if (a < cnt) dst[start + a] = k[a];
         },
         [&](int start, int cnt) {
+            if (cnt <= 32) {
+                // one member per lane, ranks by an all-pairs pass over shuffles (no memory traffic, no in-place hazard)
+                const float mine = (lane < cnt) ? __ldcg(dst + start + lane) : INFINITY;
+                int r = 0;
+                for (int b = 0; b < cnt; ++b) {
+                    const float o = __shfl_sync(0xffffffffu, mine, b);
+                    r += (o < mine || (o == mine && b < lane)) ? 1 : 0;
+                }
+                __syncwarp();
+                if (lane < cnt) dst[start + r] = mine;
+                return;
+            }
             float mn = INFINITY, mx = -INFINITY;
             for (int a = lane; a < cnt; a += 32) { const float k = __ldcg(dst + start + a); mn = fminf(mn, k); mx = fmaxf(mx, k); }
             bm_warp_minmax(mn, mx);
@@ -333,6 +345,13 @@ qm_predict_long_kernel(const PredictParams p) {
             }
         },
         [&](int start, int cnt) {
+            if (cnt <= 32) {                                 // one member per lane, all-pairs over shuffles
+                const float mine = (lane < cnt) ? key_at(start + lane) : INFINITY;
+                int r = -1;                                  // the member counts itself below
+                for (int b = 0; b < cnt; ++b) r += (__shfl_sync(0xffffffffu, mine, b) <= mine) ? 1 : 0;
+                if (lane < cnt) emit((int)P2M[start + lane], n_lo + start + r + 1);      // ties → highest rank
+                return;
+            }
             float mn = INFINITY, mx = -INFINITY;
             for (int a = lane; a < cnt; a += 32) { const float k = key_at(start + a); mn = fminf(mn, k); mx = fmaxf(mx, k); }
             bm_warp_minmax(mn, mx);
