@@ -351,6 +351,23 @@ def run_secondary(a, dev, world, rank, barrier, reduce_max, peak):
     if world == 1 and left() > 25:
         guarded('BcsdPrecipitation full grid on one GPU', c3_full)
 
+    # -- 'daily_nasa-nex' (PaddedDOYGrouper, groupers.py:19-89): 366 overlapping +-15-day pools at fit, day-of-month keyed
+    #    predict with the month-grouped 9-sample window (neighbour-table kernel) — still on the generic kernels
+    def nasanex():
+        from skdownscale_b200.pointwise_models import BcsdTemperature as BT
+        C = 4096
+        season = torch.sin(2 * torch.pi * torch.arange(T, device=dev, dtype=torch.float32) / 365.25)[:, None]
+        mk = lambda m_, a_, s_: torch.randn((T, C), device=dev, generator=gen) * s_ + m_ + a_ * season   # noqa: E731
+        xtr, ytr, xp = mk(15, 10, 3), mk(14, 12, 2), mk(16.5, 10, 3)
+        m = BT(time_grouper='daily_nasa-nex', return_anoms=False)
+        out = torch.empty((T, C), device=dev)
+        ms_fit = timed(lambda: m.fit_batched(xtr, ytr, idx), 1, 2)
+        ms_pred = timed(lambda: m.predict_batched(xp, idx, out=out), 1, 2)
+        entry(f"BcsdTemperature('daily_nasa-nex', return_anoms=False) fit+predict, {C} cells x 10950 days (generic kernels)", C, T,
+              ms_fit + ms_pred, 16, ms_fit=ms_fit, ms_predict=ms_pred)
+    if left() > 30:
+        guarded('daily_nasa-nex', nasanex)
+
     # -- configs 4 / 5: analog models, k = 10, 3 predictors; cell count per GPU = BASELINE's, or what the budget allows
     def analog(name, make, Tn, want_cells, probe_cells=2048):
         def run(Cn, steps):
@@ -363,8 +380,8 @@ def run_secondary(a, dev, world, rank, barrier, reduce_max, peak):
             return timed(lambda: m.predict_batched(Xq), 1, steps)
         ms_probe = run(probe_cells, 1)
         budget_ms = max(2.0, min(left() - 8.0, 20.0)) * 1e3 / 2.2          # warm-up + 1 timed step + generation
-        cells = int(min(want_cells, max(probe_cells, budget_ms / ms_probe * probe_cells)) // 1024 * 1024) or probe_cells
-        cells = min(cells, want_cells)
+        fit_cells = budget_ms / ms_probe * probe_cells
+        cells = want_cells if fit_cells >= want_cells else max(probe_cells, int(fit_cells) // 1024 * 1024)
         ms = run(cells, 1) if cells != probe_cells else ms_probe
         entry(f'{name}, {cells} cells/GPU x {Tn} days' + ('' if cells == want_cells else f' (BASELINE: {want_cells} cells/GPU; bounded by the bench time budget)'),
               cells, Tn, ms, 40, distance_evals_per_s=world * cells * float(Tn) * Tn / (ms * 1e-3))
