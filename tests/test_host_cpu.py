@@ -43,6 +43,35 @@ def test_abi_rejects_bad_arguments(lib):
         _lib.check(rc, 'sdb_qm_fit')
 
 
+def test_round2_entries_reject_bad_arguments(lib):
+    """The round-2 entry points validate before touching the device (no GPU needed)."""
+    rc = lib.sdb_bcsd_fit_predict(2, None, None, None, 0, 1, 1, 1, None, None, 1, 1, None, None, 1, 1, None, 0, None, None, 1,
+                                  None, None, None, None)
+    assert rc == -1 and b'NULL' in lib.sdb_last_error()
+    assert lib.sdb_series_argsort(None, 0, 1, 1, 1, None, 1, None, None) == -1
+    assert lib.sdb_analog_grid_fit(None, 0, 1, 1, 100, 3, None, None, None, None, 1, None, None) == -1
+    assert lib.sdb_analog_grid_assign(None, 0, 1, 1, 100, 3, None, None, 1, None, None) == -1
+    assert lib.sdb_peer_copy2d(None, 16, None, 16, 16, 1, 0, None) == -1
+    assert lib.sdb_peer_alloc(0, None, None) == -1
+    # what the pruned analog search covers: float32, 1..3 predictors, k <= 16, the window must fit in shared memory
+    assert lib.sdb_analog_pruned_supported(0, 18250, 3, 10) == 1
+    assert lib.sdb_analog_pruned_supported(0, 10950, 3, 200) == 0
+    assert lib.sdb_analog_pruned_supported(1, 10950, 3, 10) == 0
+    assert lib.sdb_analog_pruned_supported(0, 10950, 4, 10) == 0
+    assert lib.sdb_analog_pruned_supported(0, 30000, 3, 10) == 0
+    assert lib.sdb_analog_grid_boxes() == 512 and lib.sdb_analog_grid_planes() == 511
+    assert lib.sdb_series_argsort_max_steps() == 32768
+
+
+def test_fused_path_is_opt_in_and_scoped():
+    import torch
+    from skdownscale_b200 import engine
+    t = engine.GroupTable([(1, range(900)), (2, range(900, 1800))])
+    assert engine.fused_supported(torch.float32, t)
+    assert not engine.fused_supported(torch.float64, t)
+    assert not engine.fused_supported(torch.float32, engine.GroupTable([(0, range(1025))]))
+
+
 def test_group_tables_match_oracle():
     from skdownscale_b200.pointwise_models import groupers as g
     idx = synth.daily_index(10950)
