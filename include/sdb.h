@@ -116,6 +116,12 @@ int sdb_memcpy2d_async(void* dst, int64_t dst_pitch, const void* src, int64_t sr
 int sdb_peer_copy2d(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
                     int64_t width_bytes, int64_t height, int n_ctas, void* stream);
 
+/* One read, n_dst (1..8) peer writes: the block is stored into the same [height, width_bytes] window (pitch
+ * dst_pitch) behind every pointer of the HOST array dsts — how a rank pushes a finished cell chunk into all its
+ * peers' replicas at once.  Same alignment rule as sdb_peer_copy2d; n_ctas <= 0: 296. */
+int sdb_peer_bcast2d(void* const* dsts, int n_dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                     int64_t width_bytes, int64_t height, int n_ctas, void* stream);
+
 /* Enable direct (NVLink) access from `device` to memory of `peer_device` for kernels and copies issued on
  * `device` — required before sdb_peer_copy2d / sdb_memcpy2d_async(kind 2) touch IPC-mapped peer memory (without
  * it the kernel faults and the copy is staged through the host).  Idempotent. */

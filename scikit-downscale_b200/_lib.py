@@ -40,6 +40,7 @@ SIGNATURES = {
     'sdb_peer_open': (c_int, [c_void_p, c_void_p]),
     'sdb_peer_close': (c_int, [c_void_p]),
     'sdb_peer_free': (c_int, [c_void_p]),
+    'sdb_peer_bcast2d': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     'sdb_peer_copy2d': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     'sdb_group_mean': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
                                c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -97,3 +97,54 @@ extern "C" int sdb_peer_open(const void* handle64, void** ptr) {
 }
 extern "C" int sdb_peer_close(void* ptr) { if (ptr) SDB_CUDA_OK(cudaIpcCloseMemHandle(ptr)); return 0; }
 extern "C" int sdb_peer_free(void* ptr) { if (ptr) SDB_CUDA_OK(cudaFree(ptr)); return 0; }
+
+// ---------------------------------------------------------------- one read, n peer writes (the gather at N = 8)
+// Seven pitched copy-engine transfers per chunk, on seven streams, reached 353 GB/s received per GPU with all eight
+// GPUs pushing (profiles/r02_bench_n8_ce.json) — no better than the NCCL all-gather of round 1.  This kernel reads
+// a 16-byte element of the local block ONCE and stores it into the same place of every peer's replica: the SMs'
+// posted remote stores keep all NVLink ports busy at once.
+struct PeerDsts { uint4* p[8]; };
+__global__ void __launch_bounds__(256) peer_bcast2d_kernel(PeerDsts d, int n_dst, int64_t dst_pitch16, const uint4* __restrict__ src,
+                                                           int64_t src_pitch16, int width16, int64_t height) {
+    // a CTA walks whole rows (no 64-bit division per element); four loads in flight per thread
+    for (int64_t r = blockIdx.x; r < height; r += gridDim.x) {
+        const uint4* s = src + r * src_pitch16;
+        const int64_t at = r * dst_pitch16;
+        for (int c0 = threadIdx.x; c0 < width16; c0 += 4 * 256) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (c0 + u * 256 < width16) v[u] = __ldcs(s + c0 + u * 256);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < n_dst) {
+                    uint4* dk = d.p[k] + at;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (c0 + u * 256 < width16) dk[c0 + u * 256] = v[u];
+                }
+            }
+        }
+    }
+}
+
+extern "C" int sdb_peer_bcast2d(void* const* dsts, int n_dst, int64_t dst_pitch, const void* src, int64_t src_pitch,
+                                int64_t width_bytes, int64_t height, int n_ctas, void* stream) {
+    if (!dsts || !src || n_dst < 1 || n_dst > 8) return sdb::sdb_fail(SDB_E_INVALID, "sdb_peer_bcast2d: 1..8 destinations");
+    if (width_bytes < 0 || height < 0 || dst_pitch < width_bytes || src_pitch < width_bytes)
+        return sdb::sdb_fail(SDB_E_INVALID, "sdb_peer_bcast2d: bad geometry");
+    if (width_bytes == 0 || height == 0) return 0;
+    int64_t bits = width_bytes | dst_pitch | src_pitch | (int64_t)(uintptr_t)src;
+    PeerDsts d;
+    for (int k = 0; k < 8; ++k) {
+        d.p[k] = (k < n_dst) ? (uint4*)dsts[k] : nullptr;
+        if (k < n_dst) { if (!dsts[k]) return sdb::sdb_fail(SDB_E_INVALID, "sdb_peer_bcast2d: NULL destination"); bits |= (int64_t)(uintptr_t)dsts[k]; }
+    }
+    if (bits & 15) return sdb::sdb_fail(SDB_E_UNSUPPORTED, "sdb_peer_bcast2d: rows must be 16-byte aligned multiples of 16 bytes");
+    if (width_bytes / 16 > 0x7fffffff) return sdb::sdb_fail(SDB_E_UNSUPPORTED, "sdb_peer_bcast2d: row too long");
+    if (n_ctas <= 0) n_ctas = 296;
+    peer_bcast2d_kernel<<<n_ctas, 256, 0, (cudaStream_t)stream>>>(d, n_dst, dst_pitch / 16, (const uint4*)src, src_pitch / 16,
+                                                                (int)(width_bytes / 16), height);
+    SDB_CUDA_OK(cudaGetLastError());
+    return 0;
+}

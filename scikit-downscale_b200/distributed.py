@@ -63,7 +63,10 @@ class PeerGather:
     stream per peer) while the next chunk is still being computed.  ``method='ce'``: pitched ``cudaMemcpy2DAsync``
     on the copy engines, no SM time — 557 GB/s per direction measured between two B200s for the 129 600-cell block
     (profiles/r02_peer_copy_bench.json); ``method='kernel'``: ``sdb_peer_copy2d``, 16-byte loads / stores by
-    ``n_ctas`` CTAs (637 GB/s with 148 CTAs, 686 GB/s with 296).  No re-interleave, no second full-size buffer.
+    ``n_ctas`` CTAs (637 GB/s with 148 CTAs, 686 GB/s with 296); ``method='bcast'``: ``sdb_peer_bcast2d``, ONE kernel
+    per chunk that reads the chunk once and stores it into every peer's replica (for many peers: the seven
+    concurrent copy-engine transfers of an 8-GPU box only reach 353 GB/s received per GPU).  No re-interleave, no
+    second full-size buffer.
     The replica is allocated by the library (``sdb_peer_alloc``: an IPC handle names a whole cudaMalloc
     allocation) and wrapped as a torch tensor without a copy.
 
@@ -77,7 +80,7 @@ class PeerGather:
     """
 
     def __init__(self, n_steps: int, n_cells: int, dtype, device, n_outputs: int | None = None, group=None,
-                 method: str = 'ce', n_ctas: int = 148):
+                 method: str = 'ce', n_ctas: int = 296):
         import ctypes
         from . import _lib
         lib = _lib.load()
@@ -109,7 +112,7 @@ class PeerGather:
                     _lib.check(lib.sdb_peer_open(ctypes.create_string_buffer(h, 64), ctypes.byref(p)), 'sdb_peer_open')
                     self._opened.append(p)
                     self.peers[r] = self._wrap(p.value)      # the peer's replica, mapped for access from THIS device
-                self.streams = [torch.cuda.Stream(self.device) if r != self.rank else None for r in range(self.world)]
+                self.streams = [torch.cuda.Stream(self.device, priority=-1) if r != self.rank else None for r in range(self.world)]
         self.bytes_pushed = 0
 
     def _wrap(self, ptr: int) -> torch.Tensor:
@@ -154,6 +157,21 @@ class PeerGather:
         lead = self.full.shape[:-1]
         rows = int(torch.tensor(lead).prod().item()) if len(lead) > 1 else lead[0]
         src = self.full.view(rows, self.full.shape[-1])[:, self.a + c0:self.a + c1]
+        es = src.element_size()
+        aligned = not ((src.shape[1] * es | src.stride(0) * es | src.data_ptr()) & 15)
+        if self.method == 'bcast' and aligned and self.world <= 9:
+            # one kernel reads the chunk once and stores it into every peer's replica
+            import ctypes
+            with torch.cuda.device(self.device):
+                st = self.streams[(self.rank + 1) % self.world]
+                st.wait_event(ready)
+                order = [(self.rank + k) % self.world for k in range(1, self.world)]
+                ptrs = (ctypes.c_void_p * len(order))(*[self.peers[r].view(rows, self.full.shape[-1])[:, self.a + c0:self.a + c1].data_ptr()
+                                                       for r in order])
+                self._libmod.check(self._lib.sdb_peer_bcast2d(ptrs, len(order), self.full.shape[-1] * es, src.data_ptr(), src.stride(0) * es,
+                                                              src.shape[1] * es, rows, self.n_ctas, st.cuda_stream), 'sdb_peer_bcast2d')
+                self.bytes_pushed += len(order) * src.numel() * es
+            return
         with torch.cuda.device(self.device):
             # start with the next rank so that at any moment the eight senders aim at eight different receivers
             for k in range(1, self.world):

@@ -52,6 +52,17 @@ def _worker(rank, world, port, q):
         field2 = m.predict_gathered(Xp[:, a:b], idx, g, chunk_cells=64)
         if ok and not torch.equal(field2, ref):
             ok, why = False, 'second predict_gathered differs'
+        # the other push methods, on 16-byte aligned column blocks (SM kernel / one-read-n-writes kernel)
+        for method in ('kernel', 'bcast'):
+            C2 = 64
+            g2 = D.PeerGather(T, C2, torch.float32, dev, method=method)
+            a2, b2 = D.cell_range(C2, world, rank)
+            m2 = BcsdTemperature().fit_batched(Xtr[:, a2:b2], ytr[:, a2:b2], idx)
+            f2 = m2.predict_gathered(Xp[:, a2:b2], idx, g2, chunk_cells=16)
+            if ok and not torch.equal(f2, ref[:, :C2]):
+                ok, why = False, f'PeerGather(method={method}) differs'
+            f2 = None
+            g2.close()
         ref = ref.clone()
         field = field2 = None
         g.close()
