@@ -695,13 +695,13 @@ static int dispatch_analog(const AnalogParams& a, cudaStream_t st) {
 //     widening of the inputs — what the reference's float64 KDTree sees).
 // About 1 row in 15 is visited for 3 standard-normal predictors, k = 10, 30 years of days.
 constexpr int AC_THREADS = 512;
-constexpr int AC_K = 16;             // neighbours kept in registers
+constexpr int AC_K = 16;             // most neighbours kept in registers (list capacities built: 1, 10, 16)
 
 template <int P> constexpr size_t ac_smem_bytes(int t_fit) {
     return (size_t)t_fit * P * 4 + (size_t)(AG_BOXES + 1) * 4 + (size_t)AG_NBND * 4 + 16;
 }
 
-template <int P, bool LOGIT>
+template <int P, bool LOGIT, int KC>
 __global__ void __launch_bounds__(AC_THREADS, 1)
 analog_cell_kernel(const AnalogParams a) {
     extern __shared__ __align__(16) float ac_smem[];
@@ -751,10 +751,10 @@ analog_cell_kernel(const AnalogParams a) {
         for (int f = 0; f < 3; ++f)
             if (f < P && g[f] > 1) qb[f] = ag_slab(xqf[f], pl[f], g[f]);
         // neighbour list: ascending by (distance, training row); bpos = position in box order, row fetched on demand
-        double bd[AC_K];
-        int bpos[AC_K];
+        double bd[KC];
+        int bpos[KC];
 #pragma unroll
-        for (int i = 0; i < AC_K; ++i) { bd[i] = INFINITY; bpos[i] = -1; }
+        for (int i = 0; i < KC; ++i) { bd[i] = INFINITY; bpos[i] = -1; }
         double worst = INFINITY;
         int worst_pos = -1;
         float worstf = INFINITY;
@@ -765,7 +765,7 @@ analog_cell_kernel(const AnalogParams a) {
         };
         auto insert = [&](double d, int pos) {
 #pragma unroll
-            for (int j = AC_K - 1; j > 0; --j) {
+            for (int j = KC - 1; j > 0; --j) {
                 const bool shift = before(d, pos, bd[j - 1], bpos[j - 1]);
                 const bool here = !shift && before(d, pos, bd[j], bpos[j]);
                 const double nd = shift ? bd[j - 1] : (here ? d : bd[j]);
@@ -773,10 +773,10 @@ analog_cell_kernel(const AnalogParams a) {
                 bd[j] = nd; bpos[j] = np;
             }
             if (before(d, pos, bd[0], bpos[0])) { bd[0] = d; bpos[0] = pos; }
-            double w = bd[AC_K - 1];
-            int wp = bpos[AC_K - 1];
+            double w = bd[KC - 1];
+            int wp = bpos[KC - 1];
 #pragma unroll
-            for (int j = 0; j < AC_K; ++j) if (j == k - 1) { w = bd[j]; wp = bpos[j]; }
+            for (int j = 0; j < KC - 1; ++j) if (j == k - 1) { w = bd[j]; wp = bpos[j]; }
             worst = w; worst_pos = wp;
             worstf = isfinite(worst) ? __double2float_ru(worst * (1.0 + 1e-6)) : INFINITY;
         };
@@ -846,13 +846,13 @@ analog_cell_kernel(const AnalogParams a) {
             if (!(gmin * gmin <= worst)) break;
         }
         // rows of the neighbours, then the model's statistic
-        int li[AC_K];
-        double ld2[AC_K];
+        int li[KC];
+        double ld2[KC];
 #pragma unroll
-        for (int i = 0; i < AC_K; ++i) { li[i] = (i < k && bpos[i] >= 0) ? row_of(bpos[i]) : 0; ld2[i] = bd[i]; }
+        for (int i = 0; i < KC; ++i) { li[i] = (i < k && bpos[i] >= 0) ? row_of(bpos[i]) : 0; ld2[i] = bd[i]; }
         if (a.knn_idx) {
 #pragma unroll
-            for (int i = 0; i < AC_K; ++i) if (i < k) a.knn_idx[((int64_t)q * k + i) * a.C + c] = li[i];
+            for (int i = 0; i < KC; ++i) if (i < k) a.knn_idx[((int64_t)q * k + i) * a.C + c] = li[i];
         }
         auto idx = [&](int i) -> int { return li[i]; };
         auto dist2 = [&](int i) -> double { return ld2[i]; };
@@ -864,21 +864,23 @@ analog_cell_kernel(const AnalogParams a) {
     }
 }
 
-template <int P>
-static int launch_analog_cell(const AnalogParams& a, cudaStream_t st) {
+template <int P, bool LOGIT, int KC>
+static int launch_analog_cell_kc(const AnalogParams& a, cudaStream_t st) {
     const size_t smem = ac_smem_bytes<P>(a.t_fit);
-    const bool logit = (a.kind == SDB_ANALOG_REGRESSION) && a.has_thresh;
-    if (logit) {
-        auto kern = analog_cell_kernel<P, true>;
-        SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)a.C, AC_THREADS, smem, st>>>(a);
-    } else {
-        auto kern = analog_cell_kernel<P, false>;
-        SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)a.C, AC_THREADS, smem, st>>>(a);
-    }
+    auto kern = analog_cell_kernel<P, LOGIT, KC>;
+    SDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)a.C, AC_THREADS, smem, st>>>(a);
     SDB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <int P>
+static int launch_analog_cell(const AnalogParams& a, cudaStream_t st) {
+    const bool logit = (a.kind == SDB_ANALOG_REGRESSION) && a.has_thresh;
+    if (logit) return launch_analog_cell_kc<P, true, AC_K>(a, st);      // the threshold models keep one list capacity
+    if (a.k == 1) return launch_analog_cell_kc<P, false, 1>(a, st);
+    if (a.k <= 10) return launch_analog_cell_kc<P, false, 10>(a, st);
+    return launch_analog_cell_kc<P, false, AC_K>(a, st);
 }
 
 // largest training window the per-cell kernel can stage (227 KB of shared memory per CTA)
