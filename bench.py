@@ -609,6 +609,35 @@ def run_b200(a):
                'host_binding_rank0': numa,
                'path': 'PointWiseDownscaler.fit(X, y) + .predict(X, out=pinned) on pinned host tensors: 16384-cell chunks, H2D / kernels / D2H overlapped on three streams'}
 
+        # the host-link ceiling of the same step: the same bytes over the same pinned buffers in the same 16384-cell
+        # chunks (3 arrays H2D on one stream, 1 array D2H on another), no kernels at all — every rank at once
+        dbuf = [torch.empty((T, 16384), dtype=torch.float32, device=dev) for _ in range(2)]
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def bare_step():
+            for c0 in range(0, C, 16384):
+                c1 = min(C, c0 + 16384)
+                for k in range(3):
+                    engine.copy2d(dbuf[0][:, :c1 - c0], h[k][:, c0:c1], True, stream=s_in.cuda_stream)
+                engine.copy2d(h[3][:, c0:c1], dbuf[1][:, :c1 - c0], False, stream=s_out.cuda_stream)
+            torch.cuda.synchronize()
+
+        bare_step()
+        barrier()
+        tb0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            bare_step()
+        barrier()
+        bt = torch.tensor([(time.perf_counter() - tb0) / a.e2e_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+        bare_s = float(bt.item())
+        e2e['host_link_ceiling'] = {'ms_per_step': bare_s * 1e3, 'value': world * C * T / bare_s,
+                                    'h2d_GBps_per_rank': 3 * T * C * 4 / bare_s / 1e9, 'd2h_GBps_per_rank': T * C * 4 / bare_s / 1e9,
+                                    'e2e_over_ceiling': bare_s / step_s,
+                                    'what': 'bare cudaMemcpy2DAsync loop (sdb_memcpy2d_async): the step\'s 17 GB H2D + 5.7 GB D2H per rank over the same pinned '
+                                            'buffers and chunks, concurrently on every rank, no kernels'}
+        dbuf = None
         h = pw = None
         if old_affinity:
             os.sched_setaffinity(0, old_affinity)        # the CPU baseline below uses every core again

@@ -26,7 +26,8 @@ from .. import engine
 from .base import cuda_device
 from .bcsd import BcsdBase
 from .gard import AnalogBase, PureRegression
-from .quantile import QuantileMapper, QuantileMappingReressor
+from .quantile import (LinearTrendTransformer, QuantileMapper, QuantileMappingReressor,
+                       TrendAwareQuantileMappingRegressor)
 
 try:  # xarray is optional (absent in the build container)
     import xarray as xr
@@ -162,6 +163,10 @@ class PointWiseDownscaler:
             if x.shape[1] != 1:
                 raise ValueError('CunnaneTransformer.fit() only supports a single feature')
             model.fit_batched(x[:, 0], valid=valid)
+        elif isinstance(model, LinearTrendTransformer):
+            if x.shape[1] != 1:
+                raise ValueError('LinearTrendTransformer behind PointWiseDownscaler takes one feature per cell')
+            model.fit_batched(x[:, 0], valid=valid)
         else:
             if not args:
                 raise TypeError(f'{type(model).__name__}.fit() missing 1 required positional argument: y')
@@ -179,7 +184,7 @@ class PointWiseDownscaler:
                 model.fit_batched(x[:, 0], y[:, 0], bx.index, valid=valid)
             elif isinstance(model, (AnalogBase, PureRegression)):
                 model.fit_batched(x, y[:, 0], valid=valid)
-            elif isinstance(model, QuantileMappingReressor):
+            elif isinstance(model, (QuantileMappingReressor, TrendAwareQuantileMappingRegressor)):
                 if x.shape[1] != 1:
                     raise ValueError(f'X should have up to 1 features, found {x.shape[1]}')
                 model.fit_batched(x[:, 0], y[:, 0], valid=valid)
@@ -258,27 +263,34 @@ class PointWiseDownscaler:
             out = model.predict_batched(x[:, 0], bx.index)
             model._state.check_finite()
             return self._wrap(out, bx)
-        if isinstance(model, QuantileMappingReressor):
-            out = model.predict_batched(x[:, 0])
+        if isinstance(model, LinearTrendTransformer):
+            raise AttributeError("'LinearTrendTransformer' object has no attribute 'predict'")
+        if isinstance(model, (QuantileMappingReressor, TrendAwareQuantileMappingRegressor)):
+            out = model.predict_batched(x[:, 0]).to(x.dtype)          # core.py:129: the wrapper's array has X.dtype
             model.check_fit()
             return self._wrap(out, bx)
         out = model.predict_batched(x)
         model._check_finite()
         return self._wrap(out, bx, model.n_outputs, model.output_names)
 
-    def transform(self, X, **kwargs):
-        """core.py:340-370 for QuantileMapper."""
+    def _apply_transformer(self, X, direction, **kwargs):
         self._require_fit()
         kws = {'feature_dim': DEFAULT_FEATURE_DIM} | kwargs
         time = kws.pop('time', None)
         fd = kws.pop('feature_dim')
+        if kws:
+            raise TypeError(f'unsupported {direction} parameters on the B200 path: {sorted(kws)}')
         model = self._models
-        if not isinstance(model, QuantileMapper):
-            raise AttributeError(f"'{type(model).__name__}' object has no attribute 'transform'")
+        fn = getattr(model, direction + '_batched', None)
+        if fn is None:
+            raise AttributeError(f"'{type(model).__name__}' object has no attribute '{direction}'")
         bx = self._to_block(X, fd, time)
         x = self._float(engine.as_device(bx.data, self._dev()))
-        out = model.transform_batched(x[:, 0])
-        model._state.check_finite()
+        if x.shape[1] != 1:
+            raise ValueError(f'{type(model).__name__}.{direction} takes one feature per cell, found {x.shape[1]}')
+        out = fn(x[:, 0])
+        model._state.check_finite() if isinstance(model, QuantileMapper) else model.check_fit()
+        out = out.to(x.dtype)                            # core.py:129-131: the wrapper stores into an X.dtype array
         T = out.shape[0]
         if bx.kind == 'torch':
             return out.reshape((T,) + tuple(bx.cell_shape))
@@ -286,6 +298,14 @@ class PointWiseDownscaler:
         if bx.kind == 'numpy':
             return res.reshape((T,) + tuple(bx.cell_shape))
         return xr.DataArray(res.reshape(bx.template.shape), dims=bx.template.dims, coords=bx.template.coords)
+
+    def transform(self, X, **kwargs):
+        """core.py:340-370: ``QuantileMapper`` / ``LinearTrendTransformer`` fitted for every cell, applied to X."""
+        return self._apply_transformer(X, 'transform', **kwargs)
+
+    def inverse_transform(self, X, **kwargs):
+        """core.py:372-403 (``LinearTrendTransformer``: add the fitted trend line back)."""
+        return self._apply_transformer(X, 'inverse_transform', **kwargs)
 
     def get_attr(self, key, dtype, template_output=None):
         """core.py:405-425 for the fitted climatologies (``y_climo_``, ``_x_climo``): returns an array

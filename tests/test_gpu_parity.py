@@ -258,6 +258,68 @@ def test_linear_trend_transformer_roundtrip(dev):
     np.testing.assert_allclose(lt.transform(A), A.astype(np.float64) - line, rtol=0, atol=1e-12)
 
 
+def test_wrapper_transformers_and_trend_aware(dev, golden):
+    """PointWiseDownscaler around the remaining estimators of SURVEY 8(f)2-3: LinearTrendTransformer with
+    transform / inverse_transform (core.py:340-403; output in X.dtype, NaN cells stay NaN), and
+    TrendAwareQuantileMappingRegressor through fit / predict against the live-reference vectors."""
+    rng = np.random.default_rng(12)
+    A = (rng.standard_normal((400, 3, 5)) + np.linspace(0, 4, 400)[:, None, None]).astype(np.float32)
+    A[:, 1, 2] = np.nan                                            # a masked cell
+    pw = pm().PointWiseDownscaler(pm().LinearTrendTransformer())
+    pw.fit(A)
+    B = A[:250] + 1.0
+    Bt = pw.transform(B)
+    assert Bt.shape == B.shape and Bt.dtype == np.float32
+    assert np.isnan(Bt[:, 1, 2]).all() and np.isfinite(np.delete(Bt.reshape(250, -1), 7, axis=1)).all()
+    for (i, j) in ((0, 0), (2, 4)):
+        slope, icpt = oracle.linear_trend_fit(A[:, i, j])
+        want = B[:, i, j].astype(np.float64) - (np.arange(250) * slope + icpt)
+        np.testing.assert_allclose(Bt[:, i, j], want.astype(np.float32), rtol=0, atol=2e-6)
+    back = pw.inverse_transform(Bt)
+    ok = ~np.isnan(B)
+    np.testing.assert_allclose(back[ok], B[ok], rtol=0, atol=4e-6)
+    with pytest.raises(AttributeError):
+        pw.predict(B)
+    qm = pm().PointWiseDownscaler(pm().QuantileMapper())
+    qm.fit(A[:, 0])
+    with pytest.raises(AttributeError):
+        qm.inverse_transform(B[:, 0])
+
+    g = golden('trend_aware_qmr')
+    pw = pm().PointWiseDownscaler(pm().TrendAwareQuantileMappingRegressor(pm().QuantileMappingReressor(extrapolate='1to1', n_endpoints=6)))
+    pw.fit(g['Xtr'], g['ytr'])
+    got = pw.predict(g['Xp'])
+    assert got.dtype == g['Xp'].dtype and got.shape == g['out_1to1'].shape
+    assert_close(got, g['out_1to1'].astype(got.dtype), scale=np.std(g['ytr']))
+
+
+@pytest.mark.parametrize('kind', ['difference', 'ratio'])
+def test_edcdf_tied_inputs_multiset(dev, kind):
+    """EquidistantCdfMatcher on inputs with exact ties (precipitation-like: rounded values, a block of equal ones).
+    The reference orders tied steps by np.argsort's unstable default sort (quantile.py:607), this library by
+    (value, time index): which tied step receives which plotting position is not defined by the algorithm, so the
+    outputs must agree as a MULTISET inside every tie run and exactly (1e-5) on the untied steps."""
+    rng = np.random.default_rng(21)
+    n, C = 900, 4
+    Xtr = (rng.gamma(0.8, 6.0, (n, C)) + 0.5).astype(np.float32)
+    ytr = (rng.gamma(0.9, 5.0, (n, C)) + 0.5).astype(np.float32)
+    Xp = np.round(rng.gamma(0.8, 6.0, (n, C)) + 0.5, 0).astype(np.float32) + 1.0      # heavy ties, strictly positive
+    Xp[100:160, 1] = 3.0
+    pw = pm().PointWiseDownscaler(pm().EquidistantCdfMatcher(kind=kind, extrapolate=None))
+    pw.fit(Xtr, ytr)
+    got = pw.predict(Xp).astype(np.float64)
+    scale = np.std(ytr)
+    for c in range(C):
+        st = oracle.qm_regressor_fit(Xtr[:, c], ytr[:, c], None, 10)
+        ref = oracle.edcdf_predict(st, Xp[:, c], kind).astype(np.float32).astype(np.float64)
+        vals, inv, cnt = np.unique(Xp[:, c], return_inverse=True, return_counts=True)
+        assert (cnt > 1).sum() > 5
+        for v in range(len(vals)):
+            sel = inv == v
+            a, b = np.sort(got[sel, c]), np.sort(ref[sel])
+            assert np.all(np.abs(a - b) <= 1e-5 * np.maximum(np.abs(b), scale)), (kind, c, vals[v])
+
+
 def test_edcdf_known_answer(dev, golden):
     """The reference's own exact test (test_pointwise_models.py:323-344)."""
     x = golden('edcdf_known_answer')['x']
