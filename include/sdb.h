@@ -393,6 +393,29 @@ int sdb_pure_regression_predict(const void* X_query, int dtype, int64_t ld, int6
                                 int n_features, const double* model, void* out, int out_dtype, int64_t ld_out,
                                 const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
 
+/* ------------------------------------------------------------------ ZScoreRegressor (zscore.py:11-353)
+ * fit (zscore.py:32-66, 124-239): the record is laid out as [year, day of year] by the caller's table
+ *   day_rows[n_years * n_days] (row of the record, -1 = that year has no such day); pos_col[n_days + window] maps the
+ *   positions of the bookended year (last ceil(w/2) day columns | all | first w/2) to day columns, col_count[n_days]
+ *   is the number of years holding each column; retained window k (0 <= k < n_kept <= n_days) pools positions
+ *   k+1 .. k+window of ALL years.  shift / scale: [n_kept, ld_out] in the input dtype (mean_y - mean_X, std_y / std_X,
+ *   population std); stats (optional): [4, n_kept, ld_out] = X_mean, X_std, y_mean, y_std (fit_stats_dict_).
+ *   workspace: sdb_zscore_workspace_bytes(n_cells, n_days) bytes of device memory. */
+int64_t sdb_zscore_workspace_bytes(int64_t n_cells, int n_days);
+int sdb_zscore_fit(const void* X, const void* y, int dtype, int64_t ld, int64_t n_cells,
+                   const int32_t* day_rows, int n_years, int n_days,
+                   const int32_t* pos_col, const int32_t* col_count, int window, int n_kept,
+                   void* workspace, void* shift, void* scale, void* stats, int64_t ld_out,
+                   const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
+/* predict (zscore.py:68-110, 242-353): centred rolling mean / sample standard deviation over `window` steps (NaN where
+ * the window is incomplete), z-score, corrected with shift / scale[t mod min(n_steps, 364)].  SDB_E_INVALID when
+ * fewer than min(n_steps, 364) fitted values exist (the reference's positional IndexError, zscore.py:314). */
+int sdb_zscore_predict(const void* X, int dtype, int64_t ld, int64_t n_cells, int n_steps, int window,
+                       const void* shift, const void* scale, int64_t ld_stats, int n_stats,
+                       void* out, int out_dtype, int64_t ld_out,
+                       const uint8_t* cell_valid, int32_t* nonfinite, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

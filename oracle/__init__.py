@@ -16,8 +16,10 @@ Parity pin: the oracle is asserted against the LIVE reference estimators
 vectors committed under ``tests/golden/`` (generator:
 ``tests/golden/make_golden.py``) and against the reference's own known-answer
 tests (``skdownscale/test/test_pointwise_models.py:81-90`` quantile mapper,
-``:302-312`` padded DOY grouper, ``:323-344`` EquidistantCdfMatcher) — see
-``tests/test_oracle_golden.py``.
+``:302-312`` padded DOY grouper, ``:323-344`` EquidistantCdfMatcher, ``:236-299`` ZScoreRegressor) — see
+``tests/test_oracle_golden.py``.  One exception, stated in its header: the FIT statistics of
+``oracle/zscore.py`` restate xarray code that cannot run here and are pinned only by the reference's known-answer
+tests (predict is pinned to the live reference).
 """
 
 from .groupers import (  # noqa: F401
@@ -55,3 +57,11 @@ from .gard import (  # noqa: F401
     pure_regression_fit_predict,
 )
 from .wrapper import pointwise_fit_predict  # noqa: F401
+from .zscore import (  # noqa: F401
+    zscore_calc_stats,
+    zscore_day_table,
+    zscore_expand_index,
+    zscore_fit,
+    zscore_predict,
+    zscore_window_columns,
+)

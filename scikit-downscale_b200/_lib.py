@@ -95,6 +95,11 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p]),
     'sdb_group_trend': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'sdb_zscore_workspace_bytes': (c_int64, [c_int64, c_int]),
+    'sdb_zscore_fit': (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    'sdb_zscore_predict': (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int64, c_int,
+                                   c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     'sdb_trend_apply': (c_int, [c_int, c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int,
                                 c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     'sdb_bcsd_shift': (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,

@@ -546,6 +546,47 @@ def trend_apply(mode: int, v: torch.Tensor, table: GroupTable, slope, icpt, icpt
     return out
 
 
+@_on_device_of_first_tensor
+def zscore_fit(X: torch.Tensor, y: torch.Tensor, day_rows: np.ndarray, pos_col: np.ndarray, col_count: np.ndarray,
+               window: int, n_kept: int, valid=None, flag=None, want_stats: bool = False):
+    """ZScoreRegressor.fit for every cell (``sdb_zscore_fit``): ``shift``, ``scale`` ``[n_kept, C]`` in X's dtype
+    (+ the four fitted statistics ``[4, n_kept, C]``)."""
+    lib = _lib.load()
+    ld = _check_2d(X, 'X')
+    if y.shape != X.shape or y.dtype != X.dtype or _check_2d(y, 'y') != ld:
+        raise ValueError('zscore_fit needs X and y of one shape, dtype and row stride')
+    T, C = X.shape
+    n_years, n_days = day_rows.shape
+    dev = X.device
+    tabs = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev) for a in (day_rows, pos_col, col_count)]
+    ws = torch.empty(int(lib.sdb_zscore_workspace_bytes(C, n_days)) // 8, dtype=torch.float64, device=dev)
+    shift = torch.empty((n_kept, C), dtype=X.dtype, device=dev)
+    scale = torch.empty((n_kept, C), dtype=X.dtype, device=dev)
+    stats = torch.empty((4, n_kept, C), dtype=X.dtype, device=dev) if want_stats else None
+    _lib.check(lib.sdb_zscore_fit(_ptr(X), _ptr(y), _code(X), ld, C, _ptr(tabs[0]), n_years, n_days, _ptr(tabs[1]), _ptr(tabs[2]),
+                                  int(window), int(n_kept), _ptr(ws), _ptr(shift), _ptr(scale), _ptr(stats), C,
+                                  _ptr(valid), _ptr(flag), _stream()), 'sdb_zscore_fit')
+    return shift, scale, stats
+
+
+@_on_device_of_first_tensor
+def zscore_predict(X: torch.Tensor, shift: torch.Tensor, scale: torch.Tensor, window: int, out_dtype=None, valid=None,
+                   flag=None, out=None) -> torch.Tensor:
+    """ZScoreRegressor.predict for every cell (``sdb_zscore_predict``)."""
+    lib = _lib.load()
+    ld = _check_2d(X, 'X')
+    T, C = X.shape
+    if shift.shape != scale.shape or shift.shape[1] != C or shift.dtype != X.dtype or scale.dtype != X.dtype:
+        raise ValueError('zscore_predict: shift / scale must be [n, cells] arrays of X\'s dtype')
+    out_dtype = out_dtype or X.dtype
+    if out is None:
+        out = torch.empty((T, C), dtype=out_dtype, device=X.device)
+    ld_out = _check_2d(out, 'out')
+    _lib.check(lib.sdb_zscore_predict(_ptr(X), _code(X), ld, C, T, int(window), _ptr(shift), _ptr(scale), C, shift.shape[0],
+                                      _ptr(out), _code(out), ld_out, _ptr(valid), _ptr(flag), _stream()), 'sdb_zscore_predict')
+    return out
+
+
 def _fit_gids(st: QMFitted, table: GroupTable, device) -> torch.Tensor:
     try:
         gid = np.array([st.sort_table.key_to_gid[k] for k in table.keys], dtype=np.int32)

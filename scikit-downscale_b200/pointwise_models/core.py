@@ -28,6 +28,7 @@ from .bcsd import BcsdBase
 from .gard import AnalogBase, PureRegression
 from .quantile import (LinearTrendTransformer, QuantileMapper, QuantileMappingReressor,
                        TrendAwareQuantileMappingRegressor)
+from .zscore import ZScoreRegressor
 
 try:  # xarray is optional (absent in the build container)
     import xarray as xr
@@ -182,6 +183,12 @@ class PointWiseDownscaler:
                 if by.index is not None:
                     pd.testing.assert_index_equal(pd.Index(bx.index), pd.Index(by.index))   # base.py:17
                 model.fit_batched(x[:, 0], y[:, 0], bx.index, valid=valid)
+            elif isinstance(model, ZScoreRegressor):
+                if x.shape[1] != 1:
+                    raise ValueError(f'Zscore only supports 1 feature, found {x.shape[1]}')
+                if bx.index is None:
+                    raise ValueError('ZScoreRegressor needs the time axis labels: pass time=<DatetimeIndex>')
+                model.fit_batched(x[:, 0], y[:, 0], bx.index, valid=valid)
             elif isinstance(model, (AnalogBase, PureRegression)):
                 model.fit_batched(x, y[:, 0], valid=valid)
             elif isinstance(model, (QuantileMappingReressor, TrendAwareQuantileMappingRegressor)):
@@ -265,6 +272,12 @@ class PointWiseDownscaler:
             return self._wrap(out, bx)
         if isinstance(model, LinearTrendTransformer):
             raise AttributeError("'LinearTrendTransformer' object has no attribute 'predict'")
+        if isinstance(model, ZScoreRegressor):
+            if x.shape[1] != 1:
+                raise ValueError(f'X must have exactly 1 feature, got {x.shape[1]}')
+            out = model.predict_batched(x[:, 0])
+            model.check_fit()
+            return self._wrap(out, bx)
         if isinstance(model, (QuantileMappingReressor, TrendAwareQuantileMappingRegressor)):
             out = model.predict_batched(x[:, 0]).to(x.dtype)          # core.py:129: the wrapper's array has X.dtype
             model.check_fit()

@@ -353,6 +353,39 @@ def main():
     pr_case('pure_regression_thresh', 600, 150, 2, 62, thresh=0.0)
     pr_case('pure_regression_f64_thresh', 500, 120, 2, 63, thresh=-0.3, dtype=np.float64, p=2)
 
+    # ---- ZScoreRegressor.predict (zscore.py:68-110) through the live reference.  zscore.py imports xarray at module
+    # level (absent here) but predict never uses it: a placeholder module lets the import succeed.  fit needs xarray
+    # (_calc_stats) and cannot run — shift_ / scale_ come from the oracle's restatement (oracle/zscore.py header).
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import oracle
+    from oracle import zscore as ozs
+    if 'xarray' not in sys.modules:
+        sys.modules['xarray'] = types.ModuleType('xarray')
+    ZScoreRegressor = importlib.import_module('skdownscale.pointwise_models.zscore').ZScoreRegressor
+
+    def zs_case(name, T, Tp, C, seed, window=31, dtype=np.float32, start='1999-03-01'):
+        idx = pd.date_range(start, periods=T, freq='D')
+        Xtr, ytr, Xp = synth.temperature(max(T, Tp), C, seed=seed)
+        Xtr, ytr, Xp = Xtr[:T].astype(dtype), ytr[:T].astype(dtype), Xp[:Tp].astype(dtype)
+        idx_p = pd.date_range('2031-01-01', periods=Tp, freq='D')
+        shift, scale, out = [], [], np.empty((Tp, C), dtype=np.float64)
+        for c in range(C):
+            st = ozs.zscore_fit(Xtr[:, c], ytr[:, c], idx, window)
+            m = ZScoreRegressor(window_width=window)
+            m.shift_ = pd.Series(st['shift'])
+            m.scale_ = pd.Series(st['scale'])
+            m.n_features_in_ = 1
+            out[:, c] = np.asarray(m.predict(_df(Xp[:, c], idx_p)), dtype=np.float64)[:, 0]
+            shift.append(st['shift'])
+            scale.append(st['scale'])
+        save(name, Xtr=Xtr, ytr=ytr, Xp=Xp, start=np.array(start), window=np.int64(window),
+             shift=np.stack(shift, 1), scale=np.stack(scale, 1), out=out)
+
+    zs_case('zscore_4yr', 1461, 1461, 5, 71)
+    zs_case('zscore_pred_longer', 1200, 2000, 3, 72)
+    zs_case('zscore_w30_f64', 1100, 700, 3, 73, window=30, dtype=np.float64, start='1999-06-01')
+    zs_case('zscore_short_pred', 1461, 300, 2, 74, window=11)
+
     import sklearn
     with open(os.path.join(HERE, 'VERSIONS.json'), 'w') as f:
         json.dump({'numpy': np.__version__, 'pandas': pd.__version__, 'sklearn': sklearn.__version__,

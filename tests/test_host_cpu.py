@@ -27,7 +27,7 @@ def lib():
 def test_header_symbols_exported(lib):
     from skdownscale_b200 import _lib
     hdr = open(os.path.join(ROOT, 'include', 'sdb.h')).read()
-    declared = set(re.findall(r'^\s*(?:int|const char\*)\s+(sdb_\w+)\s*\(', hdr, flags=re.M))
+    declared = set(re.findall(r'^\s*(?:int|int64_t|const char\*)\s+(sdb_\w+)\s*\(', hdr, flags=re.M))
     assert declared == set(_lib.SIGNATURES), (declared, set(_lib.SIGNATURES))
     for name in declared:
         assert getattr(lib, name) is not None

@@ -276,3 +276,48 @@ def test_trend_aware_qm_regressor_oracle(golden, name):
         for c in range(g['Xp'].shape[1]):
             o = oracle.trend_aware_qm_fit_predict(g['Xtr'][:, c], g['ytr'][:, c], g['Xp'][:, c], ex, 6)
             _close(o[:, 0], g[key][:, c], rtol=1e-12, atol=1e-11)
+
+
+# ------------------------------------------------------------------ ZScoreRegressor (zscore.py)
+def test_zscore_reference_known_answers():
+    """The reference's own three tests (test_pointwise_models.py:236-299): a record without a 29 February gives 364
+    fitted values; y = 2 X → scale 2; X = 0, y = 1 → shift 1; unit scale / zero shift → predict is the identity
+    except for the NaN half-windows at both ends."""
+    time = pd.date_range(start='2018-01-01', end='2020-01-01')
+    x = np.linspace(0, 1, len(time))
+    st = oracle.zscore_fit(x, x * 2, time, 31)
+    assert st['scale'].shape == (364,) and st['shift'].shape == (364,)
+    np.testing.assert_allclose(st['scale'], np.full(364, 2.0))
+    st = oracle.zscore_fit(np.zeros(len(time)), np.ones(len(time)), time, 31)
+    np.testing.assert_allclose(st['shift'], np.ones(364))
+    out = oracle.zscore_predict({'shift': np.zeros(364), 'scale': np.ones(364), 'window_width': 31}, x)
+    want = x.copy()
+    want[:15] = np.nan
+    want[-15:] = np.nan
+    np.testing.assert_allclose(out, want)
+
+
+def test_zscore_window_columns():
+    """The retained windows of zscore.py:150-157,185-190 for w = 31 on a 366-column year: 365 windows; window 0 =
+    the last 15 days of the year + days 1-16; the last one = days 351-366 + days 1-15 (the wrap stays inside one
+    year's row)."""
+    cols = oracle.zscore_window_columns(366, 31)
+    assert cols.shape == (365, 31)
+    assert cols[0].tolist() == list(range(351, 366)) + list(range(0, 16))
+    assert cols[15].tolist() == list(range(0, 31))
+    assert cols[-1].tolist() == list(range(349, 366)) + list(range(0, 14))
+    assert oracle.zscore_window_columns(365, 30).shape == (363, 30)      # even window, no leap day: 363 < 364
+    tab = oracle.zscore_day_table(pd.date_range('1999-12-30', periods=400, freq='D'))
+    assert tab.shape == (3, 366) and tab[0, 363] == 0 and tab[0, 0] == -1 and tab[1, 0] == 2 and tab[1, 365] == 367
+
+
+@pytest.mark.parametrize('name', ['zscore_4yr', 'zscore_pred_longer', 'zscore_w30_f64', 'zscore_short_pred'])
+def test_zscore_predict_against_live_reference(golden, name):
+    """oracle.zscore_predict against the reference's own ZScoreRegressor.predict (zscore.py:68-110) given the same
+    shift_ / scale_."""
+    g = golden(name)
+    idx = pd.date_range(str(g['start']), periods=len(g['Xtr']), freq='D')
+    for c in range(g['Xp'].shape[1]):
+        st = oracle.zscore_fit(g['Xtr'][:, c], g['ytr'][:, c], idx, int(g['window']))
+        assert np.array_equal(st['shift'], g['shift'][:, c]) and np.array_equal(st['scale'], g['scale'][:, c])
+        _close(oracle.zscore_predict(st, g['Xp'][:, c]), g['out'][:, c], rtol=1e-12, atol=1e-12)

@@ -102,6 +102,16 @@ ta.predict_batched(engine.as_device(Xp[:700], dev))
 lt = LinearTrendTransformer()
 lt.fit_batched(engine.as_device(Xtr, dev))
 lt.inverse_transform_batched(lt.transform_batched(engine.as_device(Xp, dev)))
+# ZScoreRegressor: day-column sums, sliding windows, rolling predict (odd / even window, masked cell, short predict)
+from skdownscale_b200.pointwise_models import ZScoreRegressor  # noqa: E402
+Z = synth.temperature(1461, 7, 12)
+Z[0][:, 3] = np.nan
+for w_ in (31, 30, 5):
+    zs = ZScoreRegressor(window_width=w_)
+    zs.fit_batched(engine.as_device(Z[0], dev), engine.as_device(Z[1], dev), synth.daily_index(1461),
+                   valid=engine.cell_mask(engine.as_device(Z[0], dev)[0]), want_stats=True)
+    zs.predict_batched(engine.as_device(Z[2], dev))
+    zs.predict_batched(engine.as_device(Z[2][:200], dev), out_dtype=torch.float64)
 # the push kernels (on one device: destination = a second local buffer)
 src = torch.randn((64, 256), device=dev)
 d1, d2 = torch.zeros((64, 512), device=dev), torch.zeros((64, 512), device=dev)
