@@ -371,6 +371,22 @@ def run_secondary(a, dev, world, rank, barrier, reduce_max, peak):
     if left() > 30:
         guarded('daily_nasa-nex', nasanex)
 
+    # -- ZScoreRegressor (zscore.py): the HBM-streaming estimator of the family, per-GPU shard
+    def zscore():
+        from skdownscale_b200.pointwise_models import ZScoreRegressor
+        C = a.cells_per_gpu
+        mk = lambda m_, s_: torch.randn((T, C), device=dev, generator=gen) * s_ + m_   # noqa: E731
+        xtr, ytr, xp = mk(15, 3), mk(14, 2), mk(16.5, 3)
+        m = ZScoreRegressor()
+        out = torch.empty((T, C), device=dev)
+        ms_fit = timed(lambda: m.fit_batched(xtr, ytr, idx), 1, 3)
+        ms_pred = timed(lambda: m.predict_batched(xp, out=out), 1, 3)
+        m.check_fit()
+        entry(f'ZScoreRegressor(window_width=31) fit+predict, {C} cells x 10950 days', C, T, ms_fit + ms_pred, 16,
+              ms_fit=ms_fit, ms_predict=ms_pred, kernels='zscore_daysum_kernel + zscore_window_kernel + zscore_predict_kernel')
+    if left() > 25:
+        guarded('ZScoreRegressor', zscore)
+
     # -- configs 4 / 5: analog models, k = 10, 3 predictors; cell count per GPU = BASELINE's, or what the budget allows
     def analog(name, make, Tn, want_cells, probe_cells=2048):
         def run(Cn, steps):
