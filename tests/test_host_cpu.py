@@ -61,6 +61,44 @@ def test_round2_entries_reject_bad_arguments(lib):
     assert lib.sdb_analog_pruned_supported(0, 30000, 3, 10) == 0
     assert lib.sdb_analog_grid_boxes() == 512 and lib.sdb_analog_grid_planes() == 511
     assert lib.sdb_series_argsort_max_steps() == 32768
+    assert lib.sdb_peer_bcast2d(None, 1, 16, None, 16, 16, 1, 0, None) == -1
+    import ctypes
+    one = (ctypes.c_void_p * 1)(16)
+    assert lib.sdb_peer_bcast2d(one, 9, 16, ctypes.c_void_p(16), 16, 16, 1, 0, None) == -1        # 1..8 destinations
+    assert lib.sdb_peer_bcast2d(one, 1, 16, ctypes.c_void_p(16), 16, 24, 1, 0, None) == -1        # pitch < width
+    assert lib.sdb_peer_bcast2d(one, 1, 24, ctypes.c_void_p(16), 24, 24, 1, 0, None) == -3        # SDB_E_UNSUPPORTED: 16-byte rows only
+    assert lib.sdb_peer_bcast2d(one, 1, 16, ctypes.c_void_p(16), 16, 0, 1, 0, None) == 0          # empty block
+    assert lib.sdb_zscore_fit(None, None, 0, 1, 1, None, 1, 365, None, None, 31, 364, None, None, None, None, 1, None, None, None) == -1
+    assert b'NULL' in lib.sdb_last_error()
+    assert lib.sdb_zscore_predict(None, 0, 1, 1, 10, 31, None, None, 1, 364, None, 0, 1, None, None, None) == -1
+    assert lib.sdb_zscore_workspace_bytes(129600, 366) == 4 * 366 * 129600 * 8
+    p = ctypes.c_void_p(64)
+    # fewer fitted values than min(n_steps, 364): the reference's positional IndexError (zscore.py:314)
+    assert lib.sdb_zscore_predict(p, 0, 1, 1, 1000, 30, p, p, 1, 363, p, 0, 1, None, None, None) == -1
+    assert b'out-of-bounds' in lib.sdb_last_error()
+
+
+def test_zscore_host_tables():
+    """The calendar tables of ZScoreRegressor.fit (pointwise_models/zscore.py::day_tables) against the oracle's
+    restatement of zscore.py:124-193, and the constructor check of zscore.py:27-30."""
+    import oracle
+    from skdownscale_b200.pointwise_models import ZScoreRegressor
+    from skdownscale_b200.pointwise_models.zscore import day_tables
+    for start, T, w in (('1999-03-01', 1461, 31), ('2018-01-01', 731, 31), ('1999-06-01', 1100, 30), ('1999-03-01', 1461, 11),
+                        ('2001-01-01', 1000, 30), ('1981-01-01', 10950, 31), ('2000-02-10', 500, 1), ('2000-02-10', 500, 2)):
+        idx = pd.date_range(start, periods=T)
+        rows, pos_col, col_count, n_kept, days = day_tables(idx, w)
+        cols = oracle.zscore_window_columns(rows.shape[1], w)
+        assert n_kept == len(cols) and len(pos_col) == rows.shape[1] + w
+        assert np.array_equal(np.stack([pos_col[k + 1:k + 1 + w] for k in range(n_kept)]), cols)
+        assert np.array_equal(rows, oracle.zscore_day_table(idx))
+        assert np.array_equal(col_count, (rows >= 0).sum(0)) and col_count.sum() == T
+    assert day_tables(pd.date_range('1981-01-01', periods=10950), 31)[3] == 365
+    assert day_tables(pd.date_range('2018-01-01', '2020-01-01'), 31)[3] == 364          # the reference's own test record
+    with pytest.raises(ValueError, match='window_width must be positive'):
+        ZScoreRegressor(window_width=-3)
+    from sklearn.base import clone
+    assert clone(ZScoreRegressor(window_width=15)).get_params() == {'window_width': 15}
 
 
 def test_fused_path_is_opt_in_and_scoped():
