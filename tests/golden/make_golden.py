@@ -186,6 +186,22 @@ def main():
         ka[kind] = got
     save('edcdf_known_answer', x=xs, **ka)
 
+    # EquidistantCdfMatcher on exactly tied inputs: np.argsort's unstable order decides which tied step takes which
+    # plotting position (quantile.py:607) — pinned as a multiset per tie run (tests/test_oracle_golden.py)
+    rng = np.random.default_rng(21)
+    n, C = 900, 4
+    Xtr_t = (rng.gamma(0.8, 6.0, (n, C)) + 0.5).astype(np.float32)
+    ytr_t = (rng.gamma(0.9, 5.0, (n, C)) + 0.5).astype(np.float32)
+    Xp_t = np.round(rng.gamma(0.8, 6.0, (n, C)) + 0.5, 0).astype(np.float32) + 1.0
+    Xp_t[100:160, 1] = 3.0
+    tied = dict(Xtr=Xtr_t, ytr=ytr_t, Xp=Xp_t)
+    for kind in ('difference', 'ratio'):
+        o = np.empty((n, C), dtype=np.float32)
+        for c in range(C):
+            o[:, c] = EDC(kind=kind, extrapolate=None).fit(Xtr_t[:, c:c + 1], ytr_t[:, c]).predict(Xp_t[:, c:c + 1])
+        tied[kind] = o
+    save('edcdf_tied', **tied)
+
     # --- 2c. detrending mappers: QuantileMapper(detrend=True), BCSD qm_kwargs detrend
     def qm_detrend_case(name, Tf, Tp, C, seed, dtype=np.float32):
         _, ytr, _ = synth.temperature(Tf, C, seed, dtype)

@@ -321,3 +321,20 @@ def test_zscore_predict_against_live_reference(golden, name):
         st = oracle.zscore_fit(g['Xtr'][:, c], g['ytr'][:, c], idx, int(g['window']))
         assert np.array_equal(st['shift'], g['shift'][:, c]) and np.array_equal(st['scale'], g['scale'][:, c])
         _close(oracle.zscore_predict(st, g['Xp'][:, c]), g['out'][:, c], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize('kind', ['difference', 'ratio'])
+def test_edcdf_tied_inputs_against_live_reference(golden, kind):
+    """EquidistantCdfMatcher on exactly tied inputs (quantile.py:594-636): which tied step takes which plotting
+    position is np.argsort's unstable choice (:607), so the oracle must agree with the live reference as a MULTISET
+    inside every tie run — and therefore exactly on every untied step.  (The GPU path orders ties by time index and
+    is held to the oracle in the same way: test_gpu_parity.py::test_edcdf_tied_inputs_multiset, same inputs.)"""
+    g = golden('edcdf_tied')
+    for c in range(g['Xp'].shape[1]):
+        st = oracle.qm_regressor_fit(g['Xtr'][:, c], g['ytr'][:, c], None, 10)
+        got = oracle.edcdf_predict(st, g['Xp'][:, c], kind).astype(np.float32)
+        vals, inv, cnt = np.unique(g['Xp'][:, c], return_inverse=True, return_counts=True)
+        assert (cnt > 1).sum() > 5 and (cnt == 1).sum() > 0
+        for v in range(len(vals)):
+            sel = inv == v
+            np.testing.assert_allclose(np.sort(got[sel]), np.sort(g[kind][sel, c]), rtol=1e-6, atol=1e-6)
